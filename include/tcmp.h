@@ -1,0 +1,158 @@
+/*
+ * tcmp.h -- C ABI of libtcmp.so, the B200 (sm_100a) torque-feasibility engine.
+ *
+ * This is the drop-in boundary for the hot path of
+ * HIRO-group/torque_constrained_motion_planning.  Each entry point cites the reference
+ * interface it replaces (paths relative to the reference's src/).  The reference has no
+ * FFI for this path except the CPython extension `ikfast_panda_arm`; INTEGRATION.md shows
+ * the ctypes stubs a maintainer adds to rne.py / panda_primitives.py / ik_utils.py.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types cross the boundary.
+ *   - Unless the name ends in `_host`, every data pointer is a DEVICE pointer owned by the
+ *     caller; the library never frees caller memory and allocates nothing the caller sees.
+ *   - Batched arrays are structure-of-arrays: q[j*n + i] is joint j of state i ("[7][n]").
+ *   - Calls enqueue on `stream` (a cudaStream_t passed as void*, NULL = legacy default
+ *     stream) on the CURRENT device and return without synchronising.
+ *   - Return 0 (TCMP_OK) or a negative tcmp_status; tcmp_last_error() gives a thread-local
+ *     message.  No global mutable state: the payload mass is an input of every call (the
+ *     reference keeps it in module globals, rne.py:143-195).
+ *   - dtype: TCMP_F64 computes and stores in double (torques within 1e-9 N.m of the
+ *     reference); TCMP_F32 reads/writes float arrays and computes in float (1e-4 relative).
+ */
+#ifndef TCMP_H_
+#define TCMP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCMP_ABI_VERSION 1
+
+typedef enum {
+    TCMP_OK = 0,
+    TCMP_ERR_INVALID_ARG = -1, /* NULL where data is required, n < 0, bad enum, ... */
+    TCMP_ERR_CUDA = -2,        /* a CUDA runtime call failed; see tcmp_last_error() */
+    TCMP_ERR_NO_DEVICE = -3,   /* no usable sm_100 device */
+    TCMP_ERR_UNSUPPORTED = -4  /* combination not implemented */
+} tcmp_status;
+
+/* torque_test selector == Problem.torque_test (utils.py:86-93, panda_primitives.py:228-236) */
+typedef enum {
+    TCMP_MODE_RNE = 0, /* get_torque_limits_not_exceded_test_v4     panda_primitives.py:155-193 */
+    TCMP_MODE_NOV = 1, /* get_torque_limits_not_exceded_test_v3_nov panda_primitives.py:118-153 */
+    TCMP_MODE_DYN = 2, /* get_torque_limits_not_exceded_test_v2     panda_primitives.py:60-116  */
+    TCMP_MODE_BASE = 3 /* get_torque_limits_not_exceded_test_base   panda_primitives.py:13-16   */
+} tcmp_mode;
+
+typedef enum { TCMP_F64 = 0, TCMP_F32 = 1 } tcmp_dtype;
+
+/* The reference's closures attach the payload iff mass > 0.01 kg (panda_primitives.py:139,178);
+ * rne.add_payload attaches it iff mass > 0 (rne.py:184).  Callers pass the rule explicitly. */
+#define TCMP_PAYLOAD_THRESHOLD_TEST 0.01
+#define TCMP_PAYLOAD_THRESHOLD_RAW 0.0
+
+int tcmp_abi_version(void);
+const char *tcmp_last_error(void);
+/* Number of sm_100 devices visible, or a negative status. */
+int tcmp_device_count(void);
+
+/*
+ * Batched torque test.  Replaces rne.rne(q, qd, qdd) (rne.py:198-254) +
+ * add_payload/remove_payload (rne.py:181-195) + the limit compare of the closures
+ * (panda_primitives.py:182-188: feasible iff |tau_i| < limit_i for i in 0..5).
+ *   q, qd, qdd      [7][n]; qd/qdd may be NULL = zeros (panda_primitives.py:175-177);
+ *                   ignored in TCMP_MODE_NOV (panda_primitives.py:136-137).
+ *   payload_mass    [n] or NULL (then payload_scalar applies to every state).
+ *   payload_threshold  payload attached iff mass > threshold (rne/nov); dyn applies the
+ *                   mass unconditionally as a tool-point force (panda_primitives.py:101-110).
+ *   tau_out         [7][n] or NULL;  feasible_out [n] (1 = within limits) or NULL.
+ */
+int tcmp_rne_batch(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
+                   const void *payload_mass, double payload_scalar, double payload_threshold,
+                   void *tau_out, uint8_t *feasible_out, void *stream);
+
+/*
+ * RRT* edge check: for every edge (qa -> qb) generate n_waypoints samples of the 2-point
+ * min-jerk (min_jerk_v2.py:96-142 coefficients, :176-181 t = linspace(1/W, 1, W), :216-220
+ * x/v/a) and run the torque test on each (q, qd, qdd); first_fail_out[e] = index of the first
+ * infeasible waypoint, or n_waypoints when the edge is feasible (the prefix semantics of
+ * safe_path_force_aware, rrt_star.py:90-98, and the stop-at-first-failure of :208-210).
+ *   qa, qb [7][n_edges];  static_only != 0 tests (q, 0, 0) per waypoint as tree growth does
+ *   (rrt_star.py:95,172 call torque(q) without velocities).
+ */
+int tcmp_edge_feasibility(int mode, int dtype, int64_t n_edges, int n_waypoints, const void *qa,
+                          const void *qb, double payload_scalar, double payload_threshold,
+                          int static_only, int32_t *first_fail_out, void *stream);
+
+/*
+ * Final-trajectory check (rrt_star.py:203-210 + panda_primitives.py:299-316): evaluate the
+ * piecewise quintic with coefficients coeffs[seg][joint][6] (a0..a5, unit segment duration,
+ * min_jerk_v2.py:121-141) at samples_per_segment points t = linspace(1/S, 1, S) per segment
+ * and torque-test every sample.  Sample index s = seg*S + it.  Outputs (each may be NULL):
+ *   q_out/qd_out/qdd_out/tau_out [7][n_seg*S], feasible_out [n_seg*S],
+ *   first_fail_out[1] = first infeasible sample or n_seg*S.  first_fail_out must be
+ *   initialised by the caller to n_seg*S (the kernel atomicMin's into it).
+ */
+int tcmp_traj_feasibility(int mode, int dtype, int n_seg, int samples_per_segment,
+                          const double *coeffs, double payload_scalar, double payload_threshold,
+                          void *q_out, void *qd_out, void *qdd_out, void *tau_out,
+                          uint8_t *feasible_out, int32_t *first_fail_out, void *stream);
+
+/*
+ * Batched analytic IK for the Panda link0 -> link8 chain, joint 7 free.  Replaces
+ * ComputeIk (ikfast_panda_arm.cpp:12770; IKSolver::ComputeIk :412, rotationfunction0 :3115)
+ * and the per-solution expansion of get_ik (:12885-12902, ikfast.h:167-181).
+ *   rot9 [9][n] row-major rotation, trans3 [3][n];
+ *   free_vals [n_free][n], or [n_free] when free_broadcast != 0;
+ *   solve index s = pose*n_free + f;  sols_out [n*n_free][8][7] (may be NULL: counts only),
+ *   count_out [n*n_free] = number of solutions (0..8).
+ *   status_out [n*n_free] or NULL: bit 0 set when a solve entered a degenerate branch of the
+ *   reference's decision tree that this library resolves with its own closed form.
+ */
+int tcmp_ik_batch(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
+                  int n_free, int free_broadcast, double *sols_out, int32_t *count_out,
+                  uint8_t *status_out, void *stream);
+
+/* Batched FK, replaces ComputeFk (ikfast_panda_arm.cpp:307-395): q [7][n] -> trans3 [3][n],
+ * rot9 [9][n] (row-major), link0 -> link8. */
+int tcmp_fk_batch(int64_t n, const double *q, double *trans3, double *rot9, void *stream);
+
+/*
+ * Host-buffer variants: the call a Python/C caller makes with ordinary (ideally pinned) host
+ * arrays.  They stage through a caller-created workspace (device buffers + streams), pipeline
+ * host->device copies, kernels and device->host copies in chunks, and return after the results
+ * are in the host output arrays.
+ */
+typedef struct tcmp_workspace tcmp_workspace;
+/* chunk_states = states per pipeline stage (0 = default 1<<18). */
+int tcmp_workspace_create(tcmp_workspace **ws, int64_t chunk_states);
+int tcmp_workspace_destroy(tcmp_workspace *ws);
+int tcmp_rne_batch_host(tcmp_workspace *ws, int mode, int dtype, int64_t n, const void *q,
+                        const void *qd, const void *qdd, const void *payload_mass,
+                        double payload_scalar, double payload_threshold, void *tau_out,
+                        uint8_t *feasible_out);
+int tcmp_edge_feasibility_host(tcmp_workspace *ws, int mode, int dtype, int64_t n_edges,
+                               int n_waypoints, const void *qa, const void *qb,
+                               double payload_scalar, double payload_threshold, int static_only,
+                               int32_t *first_fail_out);
+int tcmp_ik_batch_host(tcmp_workspace *ws, int64_t n, const double *rot9, const double *trans3,
+                       const double *free_vals, int n_free, int free_broadcast, double *sols_out,
+                       int32_t *count_out, uint8_t *status_out);
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
+int tcmp_host_alloc(void **ptr, int64_t bytes);
+int tcmp_host_free(void *ptr);
+
+/* FP64 FMA throughput microbenchmark (the roofline denominator the reference never had):
+ * runs `iters` dependent-chain DFMA rounds on every SM and writes achieved FLOP/s. */
+int tcmp_fp64_peak(int iters, double *flops_out, void *stream);
+
+/* Model constants (read-only): torque limits (7), joint lower/upper (7+7), velocity limits (7). */
+int tcmp_get_limits(double *torque7, double *q_lo7, double *q_hi7, double *qd_max7);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCMP_H_ */
