@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- torque-feasibility states/s (Panda 7-DOF RNE) on N B200s, with the roofline of the
+dominant kernel, an end-to-end number through the host-buffer C-ABI call, and the CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): 1 M synthetic Panda states (q, qd, qdd, payload mass in
+{0,1,3,5} kg) per GPU, fp64, structure-of-arrays [7][n].  A step = one `rne`-mode pass of the
+torque test over the batch (tcmp_rne_batch: joint torques [7][n] + feasibility mask [n]); the `nov`
+and `dyn` modes are timed the same way and reported under "modes".  Inputs rotate over 4 distinct
+1 M-state sets (4 x 176 MB) so no step finds its inputs in the 126 MB L2.  For N > 1 the states shard
+across ranks with no data-path collective (weak scaling: 1 M states per GPU); the per-step NCCL
+all-gather of the 1 MB feasibility masks IS inside the timed region.
+
+--impl reference times the CPU implementation of the same path on the host cores: the reference's
+rne.py is pure Python/NumPy and cannot travel to the GPU box, so this arm runs the C oracle port of
+it (oracle/rne_oracle.c, validated <= 2e-13 N.m against rne.py) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_STATES = 1_000_000
+N_SETS = 4
+FLOPS_PER_STATE = 1654.0       # BASELINE.md section 4 (rne, payload > 0)
+BYTES_PER_STATE = 233.0        # 168 q/qd/qdd + 8 mass in; 56 tau + 1 mask out
+METRIC = "torque-feasibility states/sec (Panda 7-DOF RNE)"
+UNIT = "states/s"
+
+Q_LO = np.array([-2.8973, -1.7628, -2.8973, -3.0718, -2.8973, -0.0175, -2.8973])
+Q_HI = np.array([2.8973, 1.7628, 2.8973, -0.0698, 2.8973, 3.7525, 2.8973])
+V_LIM = np.array([2.175, 2.175, 2.175, 2.175, 2.61, 2.61, 2.61])
+
+
+def sample_states(n, seed):
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, n))
+    qd = rng.uniform(-V_LIM[:, None], V_LIM[:, None], size=(7, n))
+    qdd = rng.uniform(-10.0, 10.0, size=(7, n))
+    mass = rng.choice(np.array([0.0, 1.0, 3.0, 5.0]), size=n)
+    return q, qd, qdd, mass
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "configs[1]: batched RNE sweep, 1M synthetic Panda states (q, qd, qdd, payload) per GPU, "
+                    "fp64, mode rne (tau + mask); nov/dyn under 'modes'",
+        "states_per_gpu": N_STATES,
+        "layout": "SoA [7][n] fp64",
+        "l2": "inputs rotate over %d distinct 1M-state sets (%d MB) > 126 MB L2; no explicit flush"
+              % (N_SETS, N_SETS * 176),
+        "sharding": "states sharded across %d rank(s), no data-path collective; NCCL all-gather of the "
+                    "feasibility masks per step inside the timed region when N > 1" % n_gpus,
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smmax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "MEASURED_PEAKS.json"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def cpu_baseline_run(n_sample, reps, nthreads=0):
+    """C oracle port of rne.py + the limit compare, OpenMP over states, on a bounded sample."""
+    import oracle
+    q, qd, qdd, mass = sample_states(n_sample, seed=2)
+    oracle.torque_test_batch("rne", q[:, :1000], qd[:, :1000], qdd[:, :1000], mass[:1000], nthreads=nthreads)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        oracle.torque_test_batch("rne", q, qd, qdd, mass, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    cores = oracle.num_threads() if nthreads == 0 else nthreads
+    return n_sample * reps / dt, cores, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = 500_000
+    reps_per_step = 1
+    for _ in range(max(args.warmup, 1)):
+        cpu_baseline_run(50_000, 1)
+    t0 = time.perf_counter()
+    total = 0
+    cores = 1
+    for _ in range(args.steps):
+        _, cores, _ = cpu_baseline_run(n_sample, reps_per_step)
+        total += n_sample * reps_per_step
+    dt = time.perf_counter() - t0
+    value = total / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d-state seeded subsample of the 1M-state workload per step, C oracle port "
+                                   "of rne.py (the Python reference itself measures ~383 states/s/core, "
+                                   "BASELINE.md section 2)" % n_sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from torque_constrained_motion_planning_b200 import engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    # ---- synthetic inputs, resident in HBM before the timed region -------------------------------
+    sets = []
+    for s in range(N_SETS):
+        q, qd, qdd, mass = sample_states(N_STATES, seed=2 + 1000 * rank + s)
+        sets.append(tuple(torch.as_tensor(a, device=dev) for a in (q, qd, qdd, mass)))
+    host0 = sample_states(N_STATES, seed=2 + 1000 * rank)
+    gathered = torch.empty((world, N_STATES), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step(i, mode="rne"):
+        q, qd, qdd, mass = sets[i % N_SETS]
+        tau, ok = engine.torque_test_batch(q, qd, qdd, mass, mode=mode)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, ok)
+        return tau, ok
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(W):
+        step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step, K)
+    # kernel-only duration (no collective) for the roofline of the dominant kernel, same stream / events
+    ms_kernel = timed(lambda i: engine.torque_test_batch(*sets[i % N_SETS], mode="rne"), K) if world > 1 else ms_total
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * N_STATES * K / (ms_total * 1e-3)
+    kernel_s = ms_kernel * 1e-3 / K
+
+    modes = {}
+    for mode in ("nov", "dyn"):
+        for i in range(3):
+            step(i, mode)
+        ms = timed(lambda i, m=mode: step(i, m), K)
+        modes[mode] = world * N_STATES * K / (ms * 1e-3)
+    modes["rne"] = value
+    # mask-only rne (the planner's actual need: 177 B/state)
+    ms = timed(lambda i: engine.torque_test_batch(*sets[i % N_SETS], mode="rne", want_tau=False), K)
+    modes["rne_mask_only"] = world * N_STATES * K / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host arrays, H2D + D2H inside) -------
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
+    hq, hqd, hqdd, hm = (pin(a) for a in host0)
+    htau = torch.empty((7, N_STATES), dtype=torch.float64).pin_memory()
+    hok = torch.empty((N_STATES,), dtype=torch.uint8).pin_memory()
+    ws = engine.Workspace(chunk_states=1 << 17)
+    nq, nqd, nqdd, nm, ntau, nok = (t.numpy() for t in (hq, hqd, hqdd, hm, htau, hok))
+
+    def e2e_step(_i):
+        engine.torque_test_batch_host_into(ws, "rne", "f64", nq, nqd, nqdd, nm, 0.0, 0.01, ntau, nok)
+
+    for i in range(3):
+        e2e_step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * N_STATES * K / e2e_s
+    # sanity: the host path and the device path agree bit for bit on the same inputs
+    tau_d, ok_d = engine.torque_test_batch(*sets[0], mode="rne")
+    assert torch.equal(tau_d.cpu(), htau) and torch.equal(ok_d.cpu(), hok)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        fp64_peak = max(engine.fp64_peak(2048) for _ in range(3))
+        achieved_tf = FLOPS_PER_STATE * N_STATES / kernel_s / 1e12
+        achieved_gbs = BYTES_PER_STATE * N_STATES / kernel_s / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "roofline": {
+                "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                "frac": achieved_tf / (fp64_peak / 1e12), "traffic": None,
+                "peak_source": "tcmp_fp64_peak DFMA microbenchmark measured in this run (MEASURED_PEAKS.json "
+                               "carries no FP64 entry; datasheet 37.2 TFLOP/s)",
+                "flops_per_state": FLOPS_PER_STATE, "kernel": "rne_batch_kernel<double,DYN,!TOOL,tau,mask>",
+                "kernel_ms": kernel_s * 1e3,
+                "hbm": {"achieved": achieved_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                        "frac": achieved_gbs / peaks.get("hbm_gbs"), "bytes_per_state": BYTES_PER_STATE,
+                        "peak_source": peak_src},
+            },
+            "modes": modes,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(N_STATES * 176), "d2h_bytes_per_step": int(N_STATES * 57),
+                    "api": "tcmp_rne_batch_host (pinned host SoA arrays, 3-stage chunked H2D/kernel/D2H pipeline)"},
+            "gpu_launches": K,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            v, cores, dt = cpu_baseline_run(N_STATES, 3)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "3 passes over the same 1M-state workload (%.1f s wall), C oracle port of "
+                                             "rne.py with OpenMP; the Python reference itself measures ~383 "
+                                             "states/s/core (BASELINE.md section 2)" % dt}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

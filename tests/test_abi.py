@@ -1,0 +1,62 @@
+"""CPU: libtcmp.so loads and exports every symbol include/tcmp.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+from torque_constrained_motion_planning_b200 import _lib
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tcmp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tcmp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_loads():
+    from torque_constrained_motion_planning_b200 import build
+    path = build.build()
+    assert os.path.exists(path)
+    lib = _lib.load()
+    assert lib.tcmp_abi_version() == 1
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), "libtcmp.so does not export %s" % name
+    assert sorted(_lib.SIGNATURES) == declared
+
+
+def test_argument_validation_without_gpu():
+    """Invalid arguments are rejected before any CUDA call, so these run on a CPU-only box."""
+    lib = _lib.load()
+    assert lib.tcmp_rne_batch(9, 0, 1, None, None, None, None, 0.0, 0.01, None, None, None) == -1
+    assert b"bad mode" in lib.tcmp_last_error()
+    assert lib.tcmp_rne_batch(0, 7, 1, None, None, None, None, 0.0, 0.01, None, None, None) == -1
+    assert lib.tcmp_rne_batch(0, 0, -5, None, None, None, None, 0.0, 0.01, None, None, None) == -1
+    assert lib.tcmp_rne_batch(0, 0, 4, None, None, None, None, 0.0, 0.01, None, None, None) == -1  # q NULL
+    assert lib.tcmp_rne_batch(0, 0, 0, None, None, None, None, 0.0, 0.01, None, None, None) == 0   # empty batch
+    assert lib.tcmp_edge_feasibility(0, 0, 4, 0, None, None, 0.0, 0.01, 0, None, None) == -1
+    assert lib.tcmp_ik_batch(4, None, None, None, 1, 0, None, None, None, None) == -1
+    assert lib.tcmp_ik_batch(0, None, None, None, 1, 0, None, None, None, None) == 0
+
+
+def test_limits_table():
+    from torque_constrained_motion_planning_b200 import engine
+    lim = engine.get_limits()
+    assert lim["torque"].tolist() == [87, 87, 87, 87, 12, 12, 12]
+    assert np.all(lim["q_lo"] < lim["q_hi"])
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.TcmpError, match="no CPU fallback"):
+        _lib.load()

@@ -1,0 +1,269 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (libtcmp.so), against
+(a) golden vectors produced by the unmodified reference and (b) the C oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): torques <= 1e-9 N.m on the fp64 path, 1e-4 relative on the
+fp32 path; feasibility masks, first-failure indices and IK solution counts bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import load_golden, sample_edges, sample_states
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-9
+LIMITS = np.array([87.0, 87, 87, 87, 12, 12])
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from torque_constrained_motion_planning_b200 import engine
+    assert engine.device_count() >= 1
+    return engine
+
+
+def dev(x):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(x), device="cuda")
+
+
+def test_kats_from_reference(eng):
+    g = load_golden("kat_rne.npz")
+    tau, ok = eng.torque_test_batch(dev(g["q"]), dev(g["qd"]), dev(g["qdd"]), dev(g["mass"]), mode="rne")
+    assert np.abs(tau.cpu().numpy() - g["tau"]).max() < TOL64
+    assert (ok.cpu().numpy() == g["feasible"]).all()
+    # raw rne.add_payload rule (threshold 0)
+    tau, _ = eng.torque_test_batch(dev(g["q"]), dev(g["qd"]), dev(g["qdd"]), dev(g["mass"]), mode="rne",
+                                   payload_threshold=0.0)
+    assert np.abs(tau.cpu().numpy() - g["tau_raw"]).max() < TOL64
+
+
+@pytest.mark.parametrize("mode", ["rne", "nov"])
+def test_states_cfg2_vs_reference(eng, mode):
+    g = load_golden("states_cfg2.npz")
+    tau, ok = eng.torque_test_batch(dev(g["q"]), dev(g["qd"]), dev(g["qdd"]), dev(g["mass"]), mode=mode)
+    err = np.abs(tau.cpu().numpy() - g["tau_" + mode]).max()
+    assert err < TOL64, err
+    assert (ok.cpu().numpy() == g["feasible_" + mode]).all()
+
+
+@pytest.mark.parametrize("mode", ["rne", "nov", "dyn"])
+def test_200k_states_vs_oracle(eng, mode):
+    n = 200_000
+    q, qd, qdd, mass = sample_states(n, seed=2)
+    tau_o, ok_o = oracle.torque_test_batch(mode, q, qd, qdd, mass)
+    tau, ok = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode=mode)
+    tau = tau.cpu().numpy()
+    err = np.abs(tau - tau_o).max()
+    assert err < TOL64, err
+    assert (ok.cpu().numpy() == ok_o).all()
+    # no state sits within the tolerance of a limit, so the masks cannot depend on rounding
+    margin = np.abs(LIMITS[:, None] - np.abs(tau_o[:6])).min()
+    assert margin > TOL64, margin
+    # mask-only and tau-only launches agree with the combined one
+    _, ok2 = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode=mode, want_tau=False)
+    tau3, _ = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode=mode, want_mask=False)
+    assert (ok2.cpu().numpy() == ok_o).all()
+    assert np.array_equal(tau3.cpu().numpy(), tau)
+
+
+def test_static_call_without_velocities(eng):
+    """torque(q) as tree growth calls it (rrt_star.py:95): qd = qdd = None -> zeros (panda_primitives.py:175-177)."""
+    q, qd, qdd, mass = sample_states(5000, seed=7)
+    for mode in ["rne", "dyn"]:
+        tau_o, ok_o = oracle.torque_test_batch(mode, q, None, None, mass)
+        tau, ok = eng.torque_test_batch(dev(q), None, None, dev(mass), mode=mode)
+        assert np.abs(tau.cpu().numpy() - tau_o).max() < TOL64
+        assert (ok.cpu().numpy() == ok_o).all()
+        z = np.zeros_like(q)
+        tau_z, _ = eng.torque_test_batch(dev(q), dev(z), dev(z), dev(mass), mode=mode)
+        assert np.abs(tau_z.cpu().numpy() - tau_o).max() < TOL64
+
+
+def test_scalar_payload_and_base_mode(eng):
+    q, qd, qdd, _ = sample_states(3000, seed=8)
+    tau_o, ok_o = oracle.torque_test_batch("rne", q, qd, qdd, 3.0)
+    tau, ok = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), 3.0, mode="rne")
+    assert np.abs(tau.cpu().numpy() - tau_o).max() < TOL64
+    assert (ok.cpu().numpy() == ok_o).all()
+    tau, ok = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), 3.0, mode="base")
+    assert ok.cpu().numpy().all() and (tau.cpu().numpy() == 0).all()
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 127, 129, 4097])
+def test_ragged_sizes(eng, n):
+    q, qd, qdd, mass = sample_states(n, seed=100 + n)
+    tau_o, ok_o = oracle.torque_test_batch("rne", q, qd, qdd, mass)
+    tau, ok = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode="rne")
+    assert np.abs(tau.cpu().numpy() - tau_o).max() < TOL64
+    assert (ok.cpu().numpy() == ok_o).all()
+
+
+def test_empty_batch(eng):
+    import torch
+    z = torch.empty((7, 0), dtype=torch.float64, device="cuda")
+    tau, ok = eng.torque_test_batch(z, z, z, 0.0)
+    assert tau.shape == (7, 0) and ok.shape == (0,)
+
+
+def test_fp32_path(eng):
+    q, qd, qdd, mass = sample_states(50_000, seed=3)
+    tau_o, ok_o = oracle.torque_test_batch("rne", q, qd, qdd, mass)
+    tau, ok = eng.torque_test_batch(dev(q.astype(np.float32)), dev(qd.astype(np.float32)),
+                                    dev(qdd.astype(np.float32)), dev(mass.astype(np.float32)), mode="rne", dtype="f32")
+    tau = tau.cpu().numpy().astype(np.float64)
+    scale = np.maximum(np.abs(tau_o).max(axis=0, keepdims=True), 1.0)  # relative to the state's torque scale
+    rel = (np.abs(tau - tau_o) / scale).max()
+    assert rel < 1e-4, rel
+    # masks may differ only where a torque is within fp32 resolution of a limit
+    diff = ok.cpu().numpy() != ok_o
+    margin = np.abs(LIMITS[:, None] - np.abs(tau_o[:6])).min(axis=0)
+    assert (margin[diff] < 1e-2).all()
+
+
+def test_host_path_matches_device_path(eng):
+    q, qd, qdd, mass = sample_states(300_001, seed=4)
+    tau_d, ok_d = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode="rne")
+    ws = eng.Workspace(chunk_states=1 << 16)  # forces several pipeline stages + a ragged tail
+    tau_h, ok_h = eng.torque_test_batch(q, qd, qdd, mass, mode="rne", workspace=ws)
+    assert np.array_equal(tau_h, tau_d.cpu().numpy())
+    assert np.array_equal(ok_h, ok_d.cpu().numpy())
+    _, ok_h2 = eng.torque_test_batch(q, None, None, 1.0, mode="nov", want_tau=False, workspace=ws)
+    _, ok_o = oracle.torque_test_batch("nov", q, None, None, 1.0)
+    assert np.array_equal(ok_h2, ok_o)
+    ws.close()
+
+
+def test_payload_affinity_property_1m(eng):
+    """Size-independent property at the BASELINE size (1M states): the torque is affine in the payload
+    mass (the payload link's inertia is linear in m, rne.py:85-100), so tau(5) - tau(0) == 5 (tau(1) - tau(0));
+    and the mask is exactly the |tau| < limit predicate of the returned torques."""
+    n = 1_000_000
+    q, qd, qdd, _ = sample_states(n, seed=2)
+    Q, V, A = dev(q), dev(qd), dev(qdd)
+    t0, _ = eng.torque_test_batch(Q, V, A, 0.0)
+    t1, _ = eng.torque_test_batch(Q, V, A, 1.0)
+    t5, ok5 = eng.torque_test_batch(Q, V, A, 5.0)
+    lin = ((t5 - t0) - 5.0 * (t1 - t0)).abs().max().item()
+    assert lin < 1e-9, lin
+    import torch
+    lim = torch.as_tensor(LIMITS, device="cuda")[:, None]
+    pred = (t5[:6].abs() < lim).all(dim=0)
+    assert torch.equal(pred, ok5.bool())
+
+
+# ---- edges / trajectories -------------------------------------------------------------------------
+def test_edges_vs_reference(eng):
+    e = load_golden("edges_cfg4.npz")
+    ff = eng.edge_feasibility(dev(e["qa"]), dev(e["qb"]), int(e["W"]), float(e["mass"]), mode="rne")
+    assert (ff.cpu().numpy() == e["first_fail"]).all()
+
+
+@pytest.mark.parametrize("W", [64, 1, 7, 100])
+def test_edges_vs_oracle(eng, W):
+    qa, qb = sample_edges(20_000 if W == 64 else 2_000, seed=4)
+    for mode, static in [("rne", False), ("rne", True), ("nov", False), ("dyn", False)]:
+        ff_o = oracle.edge_feasibility(mode, qa, qb, W, 5.0) if not static else None
+        if static:  # tree-growth semantics: every waypoint tested as (q, 0, 0) == nov arithmetic on the same waypoints
+            ff_o = oracle.edge_feasibility("nov", qa, qb, W, 5.0)
+        ff = eng.edge_feasibility(dev(qa), dev(qb), W, 5.0, mode=mode, static_only=static)
+        assert (ff.cpu().numpy() == ff_o).all(), (mode, static, W)
+    ff_h = eng.edge_feasibility(qa, qb, W, 5.0, mode="rne")
+    assert (ff_h == oracle.edge_feasibility("rne", qa, qb, W, 5.0)).all()
+
+
+def test_edges_round_trip_property_100k(eng):
+    """BASELINE size (100k edges x 64): an edge's first failure equals the first zero of the per-state mask
+    of its 64 explicitly generated waypoints run through the state kernel."""
+    import torch
+    E, W = 100_000, 64
+    qa, qb = sample_edges(E, seed=4)
+    ff = eng.edge_feasibility(dev(qa), dev(qb), W, 5.0, mode="rne")
+    t = torch.as_tensor(np.linspace(1.0 / W, 1.0, W), device="cuda")
+    px = t ** 3 * (10 - 15 * t + 6 * t * t)
+    pv = t ** 2 * (30 - 60 * t + 30 * t * t)
+    pa = t * (60 - 180 * t + 120 * t * t)
+    A = dev(qb - qa)
+    q = (dev(qa)[:, :, None] + A[:, :, None] * px).reshape(7, -1).contiguous()
+    qd = (A[:, :, None] * pv).reshape(7, -1).contiguous()
+    qdd = (A[:, :, None] * pa).reshape(7, -1).contiguous()
+    _, ok = eng.torque_test_batch(q, qd, qdd, 5.0, want_tau=False)
+    bad = (ok.reshape(E, W) == 0)
+    first = torch.where(bad.any(dim=1), bad.float().argmax(dim=1), torch.full((E,), W, device="cuda")).int()
+    assert torch.equal(first, ff)
+
+
+def test_traj_vs_reference(eng):
+    t = load_golden("traj.npz")
+    coeffs = oracle.minjerk_coefficients(t["points"])
+    out = eng.traj_feasibility(coeffs, int(t["n_int"]), float(t["mass"]), mode="rne")
+    assert np.abs(out["q"].cpu().numpy().T - t["x"]).max() < 1e-12
+    assert np.abs(out["qd"].cpu().numpy().T - t["v"]).max() < 1e-11
+    assert np.abs(out["qdd"].cpu().numpy().T - t["a"]).max() < 1e-10
+    assert np.abs(out["tau"].cpu().numpy().T - t["tau"]).max() < TOL64
+    assert (out["feasible"].cpu().numpy() == t["feasible"]).all()
+    bad = np.nonzero(t["feasible"] == 0)[0]
+    assert out["first_fail"] == (bad[0] if len(bad) else len(t["feasible"]))
+    out0 = eng.traj_feasibility(coeffs, int(t["n_int"]), 0.0, mode="rne")
+    assert np.abs(out0["tau"].cpu().numpy().T - t["tau_nopayload"]).max() < TOL64
+
+
+# ---- IK / FK ---------------------------------------------------------------------------------------
+def _match_solutions(sols, ref, count):
+    """max over reference solutions of the distance to the nearest returned solution."""
+    worst = 0.0
+    for i in range(count):
+        d = np.abs(sols[:count] - ref[i]).max(axis=1).min()
+        worst = max(worst, d)
+    return worst
+
+
+def test_fk_vs_reference(eng):
+    g = load_golden("ik_cfg3.npz")
+    trans, rot = eng.fk_batch(dev(g["q"]))
+    assert np.abs(trans.cpu().numpy() - g["trans"]).max() < 1e-14
+    assert np.abs(rot.cpu().numpy() - g["rot"]).max() < 1e-14
+
+
+def test_ik_vs_reference_golden(eng):
+    g = load_golden("ik_cfg3.npz")
+    sols, counts, status = eng.ik_batch(dev(g["rot"]), dev(g["trans"]), dev(g["free"]))
+    sols, counts, status = sols.cpu().numpy(), counts.cpu().numpy(), status.cpu().numpy()
+    assert (counts == g["counts"]).all()                 # bit-exact solution counts
+    assert (status == 0).all()                           # random poses never touch a degenerate branch
+    worst = max(_match_solutions(sols[i], g["sols"][i], counts[i]) for i in range(len(counts)))
+    assert worst < 1e-9, worst
+    # host path (pose-chunked pipeline) gives the same bits
+    ws = eng.Workspace(chunk_states=1000)
+    s2, c2, _ = eng.ik_batch(g["rot"], g["trans"], g["free"], workspace=ws)
+    assert np.array_equal(c2, counts) and np.array_equal(s2, sols)
+
+
+def test_ik_round_trip_100k(eng):
+    """FK(IK(pose)) == pose for every returned solution (the reference's own self-check idea,
+    ikfast.py:93-102, tolerance 1e-6), and counts match the compiled reference on 100k x 3 solves."""
+    import torch
+    rng = np.random.default_rng(33)
+    n = 100_000
+    from conftest import Q_HI, Q_LO
+    q = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, n))
+    trans, rot = eng.fk_batch(dev(q))
+    free = np.stack([q[6], rng.uniform(-2.8973, 2.8973, n), rng.uniform(-2.8973, 2.8973, n)])
+    sols, counts, status = eng.ik_batch(rot, trans, dev(free))
+    _, counts_ref = oracle.ref_ik_batch(rot.cpu().numpy(), trans.cpu().numpy(), free, want_sols=False)
+    cnt = counts.cpu().numpy()
+    mism = np.nonzero(cnt != counts_ref)[0]
+    assert len(mism) == 0, (len(mism), mism[:10], cnt[mism[:10]], counts_ref[mism[:10]])
+    assert (cnt.reshape(n, 3)[:, 0] >= 1).all()          # the pose's own j7 always yields a solution
+    # round trip on the valid slots
+    valid = (torch.arange(8, device="cuda")[None, :] < counts[:, None])
+    qs = sols[valid].T.contiguous()                      # [7][m]
+    t2, r2 = eng.fk_batch(qs)
+    idx = torch.nonzero(valid)[:, 0] // 3                # pose index of each solution
+    assert (t2 - trans[:, idx]).abs().max().item() < 1e-6
+    assert (r2 - rot[:, idx]).abs().max().item() < 1e-6

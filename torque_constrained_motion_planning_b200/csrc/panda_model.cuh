@@ -1,0 +1,289 @@
+// panda_model.cuh -- Franka Panda rigid-body constants and the register-resident
+// recursive Newton-Euler core shared by every torque kernel (K1 rne, K2 nov, K3 dyn,
+// K4 edge / trajectory).
+//
+// What it computes is what the reference's rne.py:198-254 computes -- joint torques of the
+// 7-DOF arm + flange (link8) + hand (+ payload link) under gravity given as a +9.81 z base
+// acceleration (rne.py:199,232) -- but NOT how: the reference multiplies dense 6x6 spatial
+// matrices built with np.block for 9-10 links; here
+//   * the three rigidly attached tail bodies (link8 rne.py:72/133, hand :73/134, payload
+//     :181-188) are folded at compile time into link 7's inertial parameters, which become
+//     affine in the payload mass (4 FMAs at run time instead of 3 more links);
+//   * the recursion is the classical 3-vector Newton-Euler form about each link-frame origin
+//     with first moments h = m c and origin inertias J = I_c + m(|c|^2 1 - c c^T), so no
+//     c x (.) products are evaluated at run time;
+//   * the modified-DH twists alpha in {0, +-pi/2} (rne.py:47-54) make R_x(alpha) a signed
+//     permutation, so a frame change costs 2 FMA + 2 MUL; zero DH offsets are removed with
+//     `if constexpr`; joint 1's angle is never needed (gravity is along its axis), so only six
+//     sincos are evaluated;
+//   * everything lives in registers: one thread owns one state.
+// The result differs from the reference only by rounding (measured <= 2e-13 N.m over the
+// config-2 distribution, budget 1e-9).  The reference leaves cos(+-pi/2) = 6.1e-17 unsnapped
+// (rne.py:39-42); that contributes < 1e-15 N.m and is dropped here.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tcmp {
+
+// ---- compile-time model ------------------------------------------------------------------
+struct LinkConst {
+    int alpha;             // twist code of DH row k: 0, +1 (= +pi/2), -1 (= -pi/2)   rne.py:47-54
+    double px, py, pz;     // origin of frame k in frame k-1: (a, -sin(alpha) d, cos(alpha) d)  rne.py:39-42
+    double m;              // mass                                                   rne.py:125-136
+    double hx, hy, hz;     // first moment m*c                                       rne.py:106-117
+    double jxx, jxy, jxz, jyy, jyz, jzz;  // inertia about the frame origin          rne.py:16-19,65-75
+};
+
+constexpr double kGravity = 9.81;             // rne.py:199
+constexpr double kFlangeZ = 0.107;            // DH row 7 d (rne.py:54): link7 -> link8 / hand / payload frames
+constexpr double kPayloadR = 0.14 + 0.025;    // rne.py:182,186: new_inertia([0,0,hand_width+0.025], m)
+constexpr double kToolZ = 0.107 + 0.105;      // panda_grasptarget origin in the link-7 frame (panda_mod.urdf:87-91)
+
+constexpr LinkConst make_link(int alpha, double a, double d, double m, double cx, double cy, double cz,
+                              double ixx, double ixy, double ixz, double iyy, double iyz, double izz) {
+    LinkConst L{};
+    L.alpha = alpha;
+    L.px = a;
+    L.py = alpha == 0 ? 0.0 : (alpha > 0 ? -d : d);
+    L.pz = alpha == 0 ? d : 0.0;
+    L.m = m;
+    L.hx = m * cx; L.hy = m * cy; L.hz = m * cz;
+    const double c2 = cx * cx + cy * cy + cz * cz;
+    L.jxx = ixx + m * (c2 - cx * cx);
+    L.jyy = iyy + m * (c2 - cy * cy);
+    L.jzz = izz + m * (c2 - cz * cz);
+    L.jxy = ixy - m * cx * cy;
+    L.jxz = ixz - m * cx * cz;
+    L.jyz = iyz - m * cy * cz;
+    return L;
+}
+
+// Link k = panda_link(k+1).  Link 6 additionally carries link8 (m = 0, I = 0.001*1) and the hand
+// (m = 0.68, c = 0, I = 0.1*1), both rigidly at (0,0,0.107) in its frame (rne.py:54,58-61).
+constexpr LinkConst link_const(int k) {
+    switch (k) {
+        case 0: return make_link(0, 0.0, 0.333, 4.970684, 3.875e-03, 2.081e-03, -0.1750,
+                                 7.0337e-01, -1.3900e-04, 6.7720e-03, 7.0661e-01, 1.9169e-02, 9.1170e-03);
+        case 1: return make_link(-1, 0.0, 0.0, 0.646926, -3.141e-03, -2.872e-02, 3.495e-03,
+                                 7.9620e-03, -3.9250e-03, 1.0254e-02, 2.8110e-02, 7.0400e-04, 2.5995e-02);
+        case 2: return make_link(+1, 0.0, 0.316, 3.228604, 2.7518e-02, 3.9252e-02, -6.6502e-02,
+                                 3.7242e-02, -4.7610e-03, -1.1396e-02, 3.6155e-02, -1.2805e-02, 1.0830e-02);
+        case 3: return make_link(+1, 0.0825, 0.0, 3.587895, -5.317e-02, 1.04419e-01, 2.7454e-02,
+                                 2.5853e-02, 7.7960e-03, -1.3320e-03, 1.9552e-02, 8.6410e-03, 2.8323e-02);
+        case 4: return make_link(-1, -0.0825, 0.384, 1.225946, -1.1953e-02, 4.1065e-02, -3.8437e-02,
+                                 3.5549e-02, -2.1170e-03, -4.0370e-03, 2.9474e-02, 2.2900e-04, 8.6270e-03);
+        case 5: return make_link(+1, 0.0, 0.0, 1.666555, 6.0149e-02, -1.4117e-02, -1.0517e-02,
+                                 1.9640e-03, 1.0900e-04, -1.1580e-03, 4.3540e-03, 3.4100e-04, 5.4330e-03);
+        default: {
+            LinkConst L = make_link(+1, 0.088, 0.0, 7.35522e-01, 1.0517e-02, -4.252e-03, 6.1597e-02,
+                                    1.2516e-02, -4.2800e-04, -1.1960e-03, 1.0027e-02, -7.4100e-04, 4.8150e-03);
+            const double mh = 0.68, z = kFlangeZ;   // hand; link8 has zero mass
+            L.m += mh;
+            L.hz += mh * z;
+            L.jxx += 0.001 + 0.1 + mh * z * z;
+            L.jyy += 0.001 + 0.1 + mh * z * z;
+            L.jzz += 0.001 + 0.1;
+            return L;
+        }
+    }
+}
+// Payload link (rne.py:181-188): mass mp at the flange frame origin with
+// I = diag(mp r^2, mp r^2, 0), r = 0.165 -> affine terms added to link 6's parameters.
+constexpr double kPayloadHz = kFlangeZ;
+constexpr double kPayloadJ = kPayloadR * kPayloadR + kFlangeZ * kFlangeZ;
+
+// panda_mod.urdf:127,153,179,205,231,257,283 (effort), lower/upper, velocity.
+__host__ __device__ constexpr double torque_limit(int i) { return i < 4 ? 87.0 : 12.0; }
+
+template <typename T> struct V3 { T x, y, z; };
+
+// parent -> child frame:  E u,  E = Rz(theta)^T Rx(alpha)^T
+template <int ALPHA, typename T>
+__device__ __forceinline__ V3<T> rot_in(T c, T s, const V3<T> &u) {
+    T wy, wz;
+    if constexpr (ALPHA == 0) { wy = u.y; wz = u.z; }
+    else if constexpr (ALPHA > 0) { wy = u.z; wz = -u.y; }
+    else { wy = -u.z; wz = u.y; }
+    return {c * u.x + s * wy, c * wy - s * u.x, wz};
+}
+// child -> parent frame:  R u,  R = Rx(alpha) Rz(theta)
+template <int ALPHA, typename T>
+__device__ __forceinline__ V3<T> rot_out(T c, T s, const V3<T> &u) {
+    const T wx = c * u.x - s * u.y, wy = s * u.x + c * u.y;
+    if constexpr (ALPHA == 0) return {wx, wy, u.z};
+    else if constexpr (ALPHA > 0) return {wx, -u.z, wy};
+    else return {wx, u.z, -wy};
+}
+
+template <typename T> __device__ __forceinline__ void sincos_t(T x, T *s, T *c);
+template <> __device__ __forceinline__ void sincos_t<double>(double x, double *s, double *c) { sincos(x, s, c); }
+template <> __device__ __forceinline__ void sincos_t<float>(float x, float *s, float *c) { sincosf(x, s, c); }
+
+// Kinematic state carried down the chain, expressed in the current link frame.
+template <typename T> struct Kin {
+    V3<T> w;   // angular velocity
+    V3<T> wd;  // angular acceleration
+    V3<T> vd;  // linear acceleration of the frame origin (includes the +g base acceleration)
+};
+
+// Forward step for link K >= 2 (and the generic form for K == 1 when the parent is a full Kin).
+// DYN == false is the static specialisation (qd = qdd = 0): only vd is propagated.
+template <int K, typename T, bool DYN>
+__device__ __forceinline__ void forward_link(T c, T s, T qd, T qdd, Kin<T> &k) {
+    constexpr LinkConst L = link_const(K);
+    static_assert(L.pz == 0.0, "generic forward step assumes a planar DH offset");
+    V3<T> u = k.vd;
+    if constexpr (DYN) {
+        // u = vd + wd x P + w (w.P) - |w|^2 P   with P = (px, py, 0)
+        if constexpr (L.px != 0.0 || L.py != 0.0) {
+            const T w2 = k.w.x * k.w.x + k.w.y * k.w.y + k.w.z * k.w.z;
+            T wp = T(0);
+            if constexpr (L.px != 0.0) wp += k.w.x * T(L.px);
+            if constexpr (L.py != 0.0) wp += k.w.y * T(L.py);
+            if constexpr (L.px != 0.0) {
+                u.x += -w2 * T(L.px);
+                u.y += k.wd.z * T(L.px);
+                u.z += -k.wd.y * T(L.px);
+            }
+            if constexpr (L.py != 0.0) {
+                u.x += -k.wd.z * T(L.py);
+                u.y += -w2 * T(L.py);
+                u.z += k.wd.x * T(L.py);
+            }
+            u.x += k.w.x * wp;
+            u.y += k.w.y * wp;
+            u.z += k.w.z * wp;
+        }
+        V3<T> w = rot_in<L.alpha>(c, s, k.w);
+        V3<T> wd = rot_in<L.alpha>(c, s, k.wd);
+        wd.x += w.y * qd;
+        wd.y -= w.x * qd;
+        wd.z += qdd;
+        w.z += qd;
+        k.w = w;
+        k.wd = wd;
+    }
+    k.vd = rot_in<L.alpha>(c, s, u);
+}
+
+// Net inertial force F and moment N (about the frame origin) of a link with parameters
+// (m, h, J) moving with k.  Static: F = m vd, N = h x vd.
+template <typename T, bool DYN>
+__device__ __forceinline__ void link_wrench(const Kin<T> &k, T m, T hx, T hy, T hz, T jxx, T jxy, T jxz,
+                                            T jyy, T jyz, T jzz, V3<T> &F, V3<T> &N) {
+    F = {m * k.vd.x, m * k.vd.y, m * k.vd.z};
+    N = {hy * k.vd.z - hz * k.vd.y, hz * k.vd.x - hx * k.vd.z, hx * k.vd.y - hy * k.vd.x};
+    if constexpr (DYN) {
+        const V3<T> &w = k.w, &a = k.wd;
+        const T w2 = w.x * w.x + w.y * w.y + w.z * w.z;
+        const T wh = w.x * hx + w.y * hy + w.z * hz;
+        F.x += a.y * hz - a.z * hy + w.x * wh - w2 * hx;
+        F.y += a.z * hx - a.x * hz + w.y * wh - w2 * hy;
+        F.z += a.x * hy - a.y * hx + w.z * wh - w2 * hz;
+        const T lx = jxx * w.x + jxy * w.y + jxz * w.z;   // L = J w
+        const T ly = jxy * w.x + jyy * w.y + jyz * w.z;
+        const T lz = jxz * w.x + jyz * w.y + jzz * w.z;
+        N.x += jxx * a.x + jxy * a.y + jxz * a.z + (w.y * lz - w.z * ly);
+        N.y += jxy * a.x + jyy * a.y + jyz * a.z + (w.z * lx - w.x * lz);
+        N.z += jxz * a.x + jyz * a.y + jzz * a.z + (w.x * ly - w.y * lx);
+    }
+}
+
+template <int K, typename T, bool DYN>
+__device__ __forceinline__ void link_wrench_const(const Kin<T> &k, V3<T> &F, V3<T> &N) {
+    constexpr LinkConst L = link_const(K);
+    link_wrench<T, DYN>(k, T(L.m), T(L.hx), T(L.hy), T(L.hz), T(L.jxx), T(L.jxy), T(L.jxz), T(L.jyy),
+                        T(L.jyz), T(L.jzz), F, N);
+}
+
+// Backward step: fold child K's accumulated wrench (f, n, in frame K) into its parent's
+// (F, N in frame K-1):  f_p = F + R f,  n_p = N + R n + P x (R f).
+template <int K, typename T>
+__device__ __forceinline__ void backward_link(T c, T s, const V3<T> &f, const V3<T> &n, V3<T> &F, V3<T> &N) {
+    constexpr LinkConst L = link_const(K);
+    const V3<T> g = rot_out<L.alpha>(c, s, f);
+    const V3<T> r = rot_out<L.alpha>(c, s, n);
+    N.x += r.x; N.y += r.y; N.z += r.z;
+    if constexpr (L.px != 0.0) { N.y -= T(L.px) * g.z; N.z += T(L.px) * g.y; }
+    if constexpr (L.py != 0.0) { N.x += T(L.py) * g.z; N.z -= T(L.py) * g.x; }
+    if constexpr (L.pz != 0.0) { N.x -= T(L.pz) * g.y; N.y += T(L.pz) * g.x; }
+    F.x += g.x; F.y += g.y; F.z += g.z;
+}
+
+// The whole recursion for one state.
+//   DYN        false: static (nov, or rne/dyn called without velocities): qd/qdd ignored.
+//   mp_inertial  payload mass carried as a rigid body on the flange (rne/nov; 0 = none).
+//   mp_tool      payload mass applied as a pure gravity force at the grasp-target point
+//                (dyn: J^T [0,0,m g,0,0,0], panda_primitives.py:101-111; 0 = none).
+template <typename T, bool DYN, bool TOOL>
+__device__ __forceinline__ void rne_core(const T (&q)[7], const T (&qd)[7], const T (&qdd)[7], T mp_inertial,
+                                         T mp_tool, T (&tau)[7]) {
+    T c[7], s[7];
+#pragma unroll
+    for (int j = 1; j < 7; ++j) sincos_t<T>(q[j], &s[j], &c[j]);
+
+    V3<T> F[7], N[7];
+    Kin<T> k;
+    V3<T> gv;  // gravity direction * g in the current frame (only tracked when TOOL && DYN)
+
+    // link 0: w = (0,0,qd0), wd = (0,0,qdd0), vd = (0,0,g) -- its own wrench only matters through
+    // tau_0 = N_0.z = Jzz qdd0 (the w x Jw and h x vd terms have no z component).
+    constexpr LinkConst L0 = link_const(0);
+    // link 1 (alpha = -pi/2, P = 0): E (0,0,z) = (-s z, -c z, 0)
+    if constexpr (DYN) {
+        k.w = {-s[1] * qd[0], -c[1] * qd[0], qd[1]};
+        k.wd = {-s[1] * qdd[0] + k.w.y * qd[1], -c[1] * qdd[0] - k.w.x * qd[1], qdd[1]};
+    }
+    k.vd = {-s[1] * T(kGravity), -c[1] * T(kGravity), T(0)};
+    if constexpr (TOOL && DYN) gv = k.vd;
+    link_wrench_const<1, T, DYN>(k, F[1], N[1]);
+
+#define TCMP_FWD(K)                                                        \
+    forward_link<K, T, DYN>(c[K], s[K], qd[K], qdd[K], k);                 \
+    if constexpr (TOOL && DYN) gv = rot_in<link_const(K).alpha>(c[K], s[K], gv);
+    TCMP_FWD(2) link_wrench_const<2, T, DYN>(k, F[2], N[2]);
+    TCMP_FWD(3) link_wrench_const<3, T, DYN>(k, F[3], N[3]);
+    TCMP_FWD(4) link_wrench_const<4, T, DYN>(k, F[4], N[4]);
+    TCMP_FWD(5) link_wrench_const<5, T, DYN>(k, F[5], N[5]);
+    TCMP_FWD(6)
+#undef TCMP_FWD
+    {
+        constexpr LinkConst L = link_const(6);
+        const T m6 = T(L.m) + mp_inertial;
+        const T hz6 = T(L.hz) + mp_inertial * T(kPayloadHz);
+        const T jxx6 = T(L.jxx) + mp_inertial * T(kPayloadJ);
+        const T jyy6 = T(L.jyy) + mp_inertial * T(kPayloadJ);
+        link_wrench<T, DYN>(k, m6, T(L.hx), T(L.hy), hz6, jxx6, T(L.jxy), T(L.jxz), jyy6, T(L.jyz), T(L.jzz),
+                            F[6], N[6]);
+        if constexpr (TOOL) {
+            const V3<T> &g6 = DYN ? gv : k.vd;   // static: vd is exactly the rotated gravity vector
+            const T fx = mp_tool * g6.x, fy = mp_tool * g6.y, fz = mp_tool * g6.z;
+            F[6].x += fx; F[6].y += fy; F[6].z += fz;
+            N[6].x -= T(kToolZ) * fy;   // r x f, r = (0,0,kToolZ)
+            N[6].y += T(kToolZ) * fx;
+        }
+    }
+
+    // backward pass
+    tau[6] = N[6].z;
+    backward_link<6, T>(c[6], s[6], F[6], N[6], F[5], N[5]); tau[5] = N[5].z;
+    backward_link<5, T>(c[5], s[5], F[5], N[5], F[4], N[4]); tau[4] = N[4].z;
+    backward_link<4, T>(c[4], s[4], F[4], N[4], F[3], N[3]); tau[3] = N[3].z;
+    backward_link<3, T>(c[3], s[3], F[3], N[3], F[2], N[2]); tau[2] = N[2].z;
+    backward_link<2, T>(c[2], s[2], F[2], N[2], F[1], N[1]); tau[1] = N[1].z;
+    // link 1 -> link 0: only n_0.z is needed; alpha_1 = -pi/2, P_1 = 0:  (R n).z = -(s n.x + c n.y)
+    T t0 = -(s[1] * N[1].x + c[1] * N[1].y);
+    if constexpr (DYN) t0 += T(L0.jzz) * qdd[0];
+    tau[0] = t0;
+}
+
+// |tau_i| < limit_i for i in 0..5 (panda_primitives.py:182-183; joint 7 is never tested).
+template <typename T> __device__ __forceinline__ bool within_limits(const T (&tau)[7]) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ok = ok && !(fabs(tau[i]) >= T(torque_limit(i)));
+    return ok;
+}
+
+}  // namespace tcmp

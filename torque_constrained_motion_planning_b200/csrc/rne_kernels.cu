@@ -1,0 +1,94 @@
+// rne_kernels.cu -- K1 (rne), K2 (nov), K3 (dyn): batched torque test, one thread per state.
+//
+// Replaces, per state: rne.rne (rne.py:198-254) + add_payload/remove_payload (rne.py:181-195)
+// + the limit compare of the torque-test closures (panda_primitives.py:182-188).
+//
+// Data layout: structure-of-arrays [7][n] so that the 32 lanes of a warp read 32 consecutive
+// elements of each joint row (one 256 B request per row per warp, fully coalesced).  Loads are
+// streaming (ld.global.cs) and stores are st.global.cs: every byte is touched exactly once.
+// Bound: FP64 pipe: ~233 B and ~0.8 k FP64 instructions per state.
+#include "panda_model.cuh"
+#include "tcmp_internal.h"
+
+namespace tcmp {
+
+template <typename T, bool DYN, bool TOOL, bool WRITE_TAU, bool WRITE_MASK>
+__global__ void __launch_bounds__(128)
+rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, const T *__restrict__ qdd,
+                 const T *__restrict__ payload_mass, T payload_scalar, T payload_threshold,
+                 T *__restrict__ tau_out, uint8_t *__restrict__ feasible_out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T qs[7], vs[7], as[7], tau[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) qs[j] = __ldcs(q + j * n + i);
+        if constexpr (DYN) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) vs[j] = __ldcs(qd + j * n + i);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) as[j] = __ldcs(qdd + j * n + i);
+        }
+        const T mass = payload_mass ? __ldcs(payload_mass + i) : payload_scalar;
+        // rne / nov: rigid payload iff mass > threshold (panda_primitives.py:139,178; rne.py:184)
+        // dyn: the mass enters only as a tool-point gravity force (panda_primitives.py:101-111)
+        const T mp_inertial = TOOL ? T(0) : (mass > payload_threshold ? mass : T(0));
+        const T mp_tool = TOOL ? mass : T(0);
+        rne_core<T, DYN, TOOL>(qs, vs, as, mp_inertial, mp_tool, tau);
+        if constexpr (WRITE_TAU) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) __stcs(tau_out + j * n + i, tau[j]);
+        }
+        if constexpr (WRITE_MASK) __stcs(feasible_out + i, (uint8_t)within_limits<T>(tau));
+    }
+}
+
+template <typename T, bool DYN, bool TOOL, bool WT, bool WM>
+static cudaError_t launch_one(int64_t n, const void *q, const void *qd, const void *qdd, const void *pm,
+                              double ps, double pt, void *tau, uint8_t *mask, cudaStream_t st) {
+    auto kern = rne_batch_kernel<T, DYN, TOOL, WT, WM>;
+    const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, n);
+    kern<<<grid, 128, 0, st>>>(n, (const T *)q, (const T *)qd, (const T *)qdd, (const T *)pm, (T)ps, (T)pt,
+                               (T *)tau, mask);
+    return cudaGetLastError();
+}
+
+template <typename T, bool DYN, bool TOOL>
+static cudaError_t launch_outputs(int64_t n, const void *q, const void *qd, const void *qdd, const void *pm,
+                                  double ps, double pt, void *tau, uint8_t *mask, cudaStream_t st) {
+    if (tau && mask) return launch_one<T, DYN, TOOL, true, true>(n, q, qd, qdd, pm, ps, pt, tau, mask, st);
+    if (tau) return launch_one<T, DYN, TOOL, true, false>(n, q, qd, qdd, pm, ps, pt, tau, mask, st);
+    return launch_one<T, DYN, TOOL, false, true>(n, q, qd, qdd, pm, ps, pt, tau, mask, st);
+}
+
+template <typename T>
+static cudaError_t launch_typed(int mode, int64_t n, const void *q, const void *qd, const void *qdd,
+                                const void *pm, double ps, double pt, void *tau, uint8_t *mask,
+                                cudaStream_t st) {
+    // Without both velocity arrays the reference tests the static state (panda_primitives.py:175-177);
+    // nov always does (panda_primitives.py:136-137).
+    const bool dynamic = (mode != TCMP_MODE_NOV) && qd && qdd;
+    const bool tool = (mode == TCMP_MODE_DYN);
+    if (dynamic) {
+        if (tool) return launch_outputs<T, true, true>(n, q, qd, qdd, pm, ps, pt, tau, mask, st);
+        return launch_outputs<T, true, false>(n, q, qd, qdd, pm, ps, pt, tau, mask, st);
+    }
+    if (tool) return launch_outputs<T, false, true>(n, q, qd, qdd, pm, ps, pt, tau, mask, st);
+    return launch_outputs<T, false, false>(n, q, qd, qdd, pm, ps, pt, tau, mask, st);
+}
+
+cudaError_t launch_rne_batch(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
+                             const void *pm, double ps, double pt, void *tau, uint8_t *mask,
+                             cudaStream_t st) {
+    if (mode == TCMP_MODE_BASE) {  // panda_primitives.py:13-16: always feasible, no torques computed
+        cudaError_t e = cudaSuccess;
+        if (mask) e = launch_fill<uint8_t>(n, mask, 1, st);
+        if (tau && e == cudaSuccess)
+            e = dtype == TCMP_F64 ? launch_fill<double>(7 * n, (double *)tau, 0.0, st)
+                                  : launch_fill<float>(7 * n, (float *)tau, 0.f, st);
+        return e;
+    }
+    if (dtype == TCMP_F64) return launch_typed<double>(mode, n, q, qd, qdd, pm, ps, pt, tau, mask, st);
+    return launch_typed<float>(mode, n, q, qd, qdd, pm, ps, pt, tau, mask, st);
+}
+
+}  // namespace tcmp

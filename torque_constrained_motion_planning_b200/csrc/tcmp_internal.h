@@ -1,0 +1,50 @@
+// tcmp_internal.h -- declarations shared by the kernel translation units and the C-ABI shim.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tcmp.h"
+
+namespace tcmp {
+
+// Persistent-style grid: enough CTAs to fill every SM at the kernel's occupancy, never more
+// than the work needs.  148 SMs on B200; the count is read from the device so a grid is always
+// a whole number of waves.
+int grid_for(const void *kernel, int block, int64_t n_threads_needed);
+int sm_count();
+
+// out[i] = v for i < n (used by the `base` torque test, which is constant-true).
+template <typename T> __global__ void fill_kernel(int64_t n, T *out, T v) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
+}
+template <typename T> inline cudaError_t launch_fill(int64_t n, T *out, T v, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const int64_t want = (n + 255) / 256;
+    const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    fill_kernel<T><<<grid, 256, 0, st>>>(n, out, v);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rne_batch(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
+                             const void *payload_mass, double payload_scalar, double payload_threshold,
+                             void *tau_out, uint8_t *feasible_out, cudaStream_t st);
+
+cudaError_t launch_edge_feasibility(int mode, int dtype, int64_t n_edges, int n_waypoints, const void *qa,
+                                    const void *qb, double payload_scalar, double payload_threshold,
+                                    int static_only, int32_t *first_fail_out, cudaStream_t st);
+
+cudaError_t launch_traj_feasibility(int mode, int dtype, int n_seg, int samples_per_segment,
+                                    const double *coeffs, double payload_scalar, double payload_threshold,
+                                    void *q_out, void *qd_out, void *qdd_out, void *tau_out,
+                                    uint8_t *feasible_out, int32_t *first_fail_out, cudaStream_t st);
+
+cudaError_t launch_ik_batch(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
+                            int n_free, int free_broadcast, double *sols_out, int32_t *count_out,
+                            uint8_t *status_out, cudaStream_t st);
+
+cudaError_t launch_fk_batch(int64_t n, const double *q, double *trans3, double *rot9, cudaStream_t st);
+
+cudaError_t launch_fp64_peak(int iters, double *sink, int *grid_out, int *block_out, cudaStream_t st);
+
+}  // namespace tcmp

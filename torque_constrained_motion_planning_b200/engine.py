@@ -1,0 +1,286 @@
+"""Batched Python entry points over the C-ABI (include/tcmp.h).
+
+Two calling conventions, chosen by the type of the first array argument:
+
+* **device**: ``torch`` CUDA tensors in, ``torch`` CUDA tensors out.  Zero-copy: only
+  ``data_ptr()`` and the current stream cross into libtcmp.so.
+* **host**: NumPy arrays (or CPU tensors) in, NumPy arrays out, staged through a
+  :class:`Workspace` (pinned-or-pageable host memory -> chunked H2D / kernel / D2H pipeline).
+
+All state arrays are structure-of-arrays ``[7][n]`` (joint-major), the layout the kernels read
+coalesced.  Nothing here computes torques on the CPU; without a B200 and libtcmp.so every call
+raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import DTYPE, MODE, PAYLOAD_THRESHOLD_TEST, TcmpError, check, load
+
+_NP = {"f64": np.float64, "f32": np.float32}
+
+
+def _is_cuda_tensor(x) -> bool:
+    return hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _tdtype(dtype):
+    torch = _torch()
+    return {"f64": torch.float64, "f32": torch.float32}[dtype]
+
+
+def _ptr(t) -> Optional[int]:
+    return None if t is None else int(t.data_ptr())
+
+
+def _nptr(a) -> Optional[int]:
+    return None if a is None else int(a.ctypes.data)
+
+
+def _stream_ptr() -> int:
+    return int(_torch().cuda.current_stream().cuda_stream)
+
+
+def _as_dev(x, dtype, shape, device):
+    torch = _torch()
+    if x is None:
+        return None
+    if not torch.is_tensor(x):
+        x = torch.as_tensor(np.asarray(x), device=device)
+    x = x.to(device=device, dtype=_tdtype(dtype)).contiguous()
+    if tuple(x.shape) != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (tuple(shape), tuple(x.shape)))
+    return x
+
+
+def _as_host(x, dtype, shape):
+    if x is None:
+        return None
+    if hasattr(x, "numpy") and not isinstance(x, np.ndarray):
+        x = x.numpy()
+    a = np.ascontiguousarray(x, dtype=_NP[dtype])
+    if a.shape != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (tuple(shape), a.shape))
+    return a
+
+
+class Workspace:
+    """Device staging buffers + streams for the host-array entry points (tcmp_workspace)."""
+
+    def __init__(self, chunk_states: int = 0):
+        self._h = ctypes.c_void_p()
+        check(load().tcmp_workspace_create(ctypes.byref(self._h), int(chunk_states)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            load().tcmp_workspace_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ws: Optional[Workspace] = None
+
+
+def default_workspace() -> Workspace:
+    global _default_ws
+    if _default_ws is None:
+        _default_ws = Workspace()
+    return _default_ws
+
+
+def device_count() -> int:
+    n = load().tcmp_device_count()
+    if n < 0:
+        raise TcmpError("no CUDA device: %s" % load().tcmp_last_error().decode())
+    return n
+
+
+def torque_test_batch(q, qd=None, qdd=None, payload_mass=0.0, mode: str = "rne", dtype: str = "f64",
+                      payload_threshold: float = PAYLOAD_THRESHOLD_TEST, want_tau: bool = True,
+                      want_mask: bool = True, workspace: Optional[Workspace] = None):
+    """Batched torque test (tcmp_rne_batch).  q/qd/qdd ``[7][n]``; payload_mass scalar or ``[n]``.
+    Returns ``(tau [7][n] or None, feasible uint8 [n] or None)``."""
+    lib = load()
+    if not (want_tau or want_mask):
+        raise ValueError("nothing to compute")
+    n = int(q.shape[1])
+    scalar = 0.0
+    pm = None
+    if np.ndim(payload_mass) == 0:
+        scalar = float(payload_mass)
+    else:
+        pm = payload_mass
+    if _is_cuda_tensor(q):
+        torch = _torch()
+        dev = q.device
+        with torch.cuda.device(dev):
+            qt = _as_dev(q, dtype, (7, n), dev)
+            qdt = _as_dev(qd, dtype, (7, n), dev)
+            qddt = _as_dev(qdd, dtype, (7, n), dev)
+            pmt = _as_dev(pm, dtype, (n,), dev)
+            tau = torch.empty((7, n), dtype=_tdtype(dtype), device=dev) if want_tau else None
+            mask = torch.empty((n,), dtype=torch.uint8, device=dev) if want_mask else None
+            check(lib.tcmp_rne_batch(MODE[mode], DTYPE[dtype], n, _ptr(qt), _ptr(qdt), _ptr(qddt), _ptr(pmt), scalar,
+                                     float(payload_threshold), _ptr(tau), _ptr(mask), _stream_ptr()))
+        return tau, mask
+    ws = workspace or default_workspace()
+    qa = _as_host(q, dtype, (7, n))
+    qda = _as_host(qd, dtype, (7, n))
+    qdda = _as_host(qdd, dtype, (7, n))
+    pma = _as_host(pm, dtype, (n,))
+    tau = np.empty((7, n), dtype=_NP[dtype]) if want_tau else None
+    mask = np.empty((n,), dtype=np.uint8) if want_mask else None
+    check(lib.tcmp_rne_batch_host(ws.handle, MODE[mode], DTYPE[dtype], n, _nptr(qa), _nptr(qda), _nptr(qdda),
+                                  _nptr(pma), scalar, float(payload_threshold), _nptr(tau), _nptr(mask)))
+    return tau, mask
+
+
+def torque_test_batch_host_into(ws: Workspace, mode, dtype, q, qd, qdd, payload_mass, payload_scalar,
+                                payload_threshold, tau_out, mask_out) -> None:
+    """Allocation-free host call for benchmarking: every array is a preallocated (pinned) ndarray."""
+    n = int(q.shape[1])
+    check(load().tcmp_rne_batch_host(ws.handle, MODE[mode], DTYPE[dtype], n, _nptr(q), _nptr(qd), _nptr(qdd),
+                                     _nptr(payload_mass), float(payload_scalar), float(payload_threshold),
+                                     _nptr(tau_out), _nptr(mask_out)))
+
+
+def edge_feasibility(qa, qb, n_waypoints: int = 64, payload_mass: float = 0.0, mode: str = "rne",
+                     dtype: str = "f64", payload_threshold: float = PAYLOAD_THRESHOLD_TEST,
+                     static_only: bool = False, workspace: Optional[Workspace] = None):
+    """RRT* edge check (tcmp_edge_feasibility): first infeasible min-jerk waypoint per edge
+    (== n_waypoints when the edge is feasible).  qa/qb ``[7][n_edges]``."""
+    lib = load()
+    n = int(qa.shape[1])
+    if _is_cuda_tensor(qa):
+        torch = _torch()
+        dev = qa.device
+        with torch.cuda.device(dev):
+            a = _as_dev(qa, dtype, (7, n), dev)
+            b = _as_dev(qb, dtype, (7, n), dev)
+            ff = torch.empty((n,), dtype=torch.int32, device=dev)
+            check(lib.tcmp_edge_feasibility(MODE[mode], DTYPE[dtype], n, int(n_waypoints), _ptr(a), _ptr(b),
+                                            float(payload_mass), float(payload_threshold), int(static_only),
+                                            _ptr(ff), _stream_ptr()))
+        return ff
+    ws = workspace or default_workspace()
+    a = _as_host(qa, dtype, (7, n))
+    b = _as_host(qb, dtype, (7, n))
+    ff = np.empty((n,), dtype=np.int32)
+    check(lib.tcmp_edge_feasibility_host(ws.handle, MODE[mode], DTYPE[dtype], n, int(n_waypoints), _nptr(a),
+                                         _nptr(b), float(payload_mass), float(payload_threshold),
+                                         int(static_only), _nptr(ff)))
+    return ff
+
+
+def traj_feasibility(coeffs, samples_per_segment: int, payload_mass: float = 0.0, mode: str = "rne",
+                     dtype: str = "f64", payload_threshold: float = PAYLOAD_THRESHOLD_TEST,
+                     want_samples: bool = True, want_tau: bool = True, device=None):
+    """Final-trajectory check (tcmp_traj_feasibility) on min-jerk coefficients ``[n_seg][7][6]``.
+    Returns dict(q, qd, qdd, tau  [7][n] tensors or None, feasible uint8 [n], first_fail int)."""
+    torch = _torch()
+    lib = load()
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    c = np.ascontiguousarray(coeffs, dtype=np.float64)
+    n_seg = c.shape[0]
+    if c.shape != (n_seg, 7, 6):
+        raise ValueError("coeffs must be [n_seg][7][6]")
+    S = int(samples_per_segment)
+    n = n_seg * S
+    with torch.cuda.device(dev):
+        ct = torch.as_tensor(c, device=dev)
+        td = _tdtype(dtype)
+        mk = (lambda: torch.empty((7, n), dtype=td, device=dev))
+        q = mk() if want_samples else None
+        qd = mk() if want_samples else None
+        qdd = mk() if want_samples else None
+        tau = mk() if want_tau else None
+        mask = torch.empty((n,), dtype=torch.uint8, device=dev)
+        ff = torch.full((1,), n, dtype=torch.int32, device=dev)
+        check(lib.tcmp_traj_feasibility(MODE[mode], DTYPE[dtype], n_seg, S, _ptr(ct), float(payload_mass),
+                                        float(payload_threshold), _ptr(q), _ptr(qd), _ptr(qdd), _ptr(tau),
+                                        _ptr(mask), _ptr(ff), _stream_ptr()))
+        first = int(ff.item())
+    return {"q": q, "qd": qd, "qdd": qdd, "tau": tau, "feasible": mask, "first_fail": first}
+
+
+def ik_batch(rot9, trans3, free, want_sols: bool = True, want_status: bool = True,
+             workspace: Optional[Workspace] = None):
+    """Batched IK (tcmp_ik_batch).  rot9 ``[9][n]``, trans3 ``[3][n]``, free ``[n_free][n]`` or
+    ``[n_free]`` (broadcast).  Returns ``(sols [n*n_free][8][7] or None, counts int32, status uint8 or None)``
+    with solve index ``pose*n_free + f``."""
+    lib = load()
+    n = int(rot9.shape[1])
+    bcast = int(len(free.shape) == 1)
+    n_free = int(free.shape[0])
+    fshape = (n_free,) if bcast else (n_free, n)
+    if _is_cuda_tensor(rot9):
+        torch = _torch()
+        dev = rot9.device
+        with torch.cuda.device(dev):
+            r = _as_dev(rot9, "f64", (9, n), dev)
+            t = _as_dev(trans3, "f64", (3, n), dev)
+            f = _as_dev(free, "f64", fshape, dev)
+            sols = torch.empty((n * n_free, 8, 7), dtype=torch.float64, device=dev) if want_sols else None
+            counts = torch.empty((n * n_free,), dtype=torch.int32, device=dev)
+            status = torch.empty((n * n_free,), dtype=torch.uint8, device=dev) if want_status else None
+            check(lib.tcmp_ik_batch(n, _ptr(r), _ptr(t), _ptr(f), n_free, bcast, _ptr(sols), _ptr(counts),
+                                    _ptr(status), _stream_ptr()))
+        return sols, counts, status
+    ws = workspace or default_workspace()
+    r = _as_host(rot9, "f64", (9, n))
+    t = _as_host(trans3, "f64", (3, n))
+    f = _as_host(free, "f64", fshape)
+    sols = np.empty((n * n_free, 8, 7), dtype=np.float64) if want_sols else None
+    counts = np.empty((n * n_free,), dtype=np.int32)
+    status = np.empty((n * n_free,), dtype=np.uint8) if want_status else None
+    check(lib.tcmp_ik_batch_host(ws.handle, n, _nptr(r), _nptr(t), _nptr(f), n_free, bcast, _nptr(sols),
+                                 _nptr(counts), _nptr(status)))
+    return sols, counts, status
+
+
+def fk_batch(q):
+    """Batched FK (tcmp_fk_batch): q ``[7][n]`` -> (trans3 ``[3][n]``, rot9 ``[9][n]``)."""
+    torch = _torch()
+    lib = load()
+    host = not _is_cuda_tensor(q)
+    dev = torch.device("cuda", torch.cuda.current_device()) if host else q.device
+    n = int(q.shape[1])
+    with torch.cuda.device(dev):
+        qt = _as_dev(q, "f64", (7, n), dev)
+        trans = torch.empty((3, n), dtype=torch.float64, device=dev)
+        rot = torch.empty((9, n), dtype=torch.float64, device=dev)
+        check(lib.tcmp_fk_batch(n, _ptr(qt), _ptr(trans), _ptr(rot), _stream_ptr()))
+    if host:
+        return trans.cpu().numpy(), rot.cpu().numpy()
+    return trans, rot
+
+
+def fp64_peak(iters: int = 4096) -> float:
+    """Measured FP64 FMA throughput of the current device in FLOP/s (tcmp_fp64_peak)."""
+    out = ctypes.c_double(0.0)
+    check(load().tcmp_fp64_peak(int(iters), ctypes.byref(out), None))
+    return float(out.value)
+
+
+def get_limits():
+    tq, lo, hi, vm = (np.empty(7) for _ in range(4))
+    check(load().tcmp_get_limits(_nptr(tq), _nptr(lo), _nptr(hi), _nptr(vm)))
+    return {"torque": tq, "q_lo": lo, "q_hi": hi, "qd_max": vm}
