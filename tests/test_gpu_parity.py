@@ -104,6 +104,31 @@ def test_ragged_sizes(eng, n):
     assert (ok.cpu().numpy() == ok_o).all()
 
 
+def test_large_and_nonfinite_angles_take_the_exact_path(eng):
+    """The hot loop's branch-free sincos covers |q| < 1e5 rad; anything larger is redone with CUDA's
+    sincos() (exact argument reduction), so parity with libm holds for absurd angles too, and NaN/inf
+    propagate like the reference (NaN torque -> the `>=` compare is False -> feasible)."""
+    q, qd, qdd, mass = sample_states(4096, seed=9)
+    rng = np.random.default_rng(9)
+    big = rng.choice(4096, size=300, replace=False)
+    q[rng.integers(1, 7, size=300), big] = rng.uniform(-1, 1, size=300) * 10.0 ** rng.uniform(5, 15, size=300)
+    q[3, 17] = 99999.99999   # just inside the fast range
+    q[3, 18] = 100000.0      # first value outside
+    tau_o, ok_o = oracle.torque_test_batch("rne", q, qd, qdd, mass)
+    tau, ok = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode="rne")
+    assert np.abs(tau.cpu().numpy() - tau_o).max() < TOL64
+    assert (ok.cpu().numpy() == ok_o).all()
+    q[2, 5] = np.nan
+    q[4, 6] = np.inf
+    tau, ok = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode="rne")
+    t = tau.cpu().numpy()
+    assert np.isnan(t[:, 5]).any() and np.isnan(t[:, 6]).any()
+    good = np.ones(4096, bool); good[[5, 6]] = False
+    assert np.abs(t[:, good] - tau_o[:, good]).max() < TOL64
+    tau_o2, ok_o2 = oracle.torque_test_batch("rne", q, qd, qdd, mass)
+    assert (ok.cpu().numpy() == ok_o2).all()
+
+
 def test_empty_batch(eng):
     import torch
     z = torch.empty((7, 0), dtype=torch.float64, device="cuda")

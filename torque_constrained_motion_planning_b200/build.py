@@ -42,11 +42,13 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), suffix: str = "") -> str:
+    """defines/suffix build an experimental variant (libtcmp<suffix>.so) next to the product library."""
+    lib_path = LIB if not suffix else os.path.join(HERE, "libtcmp%s.so" % suffix)
+    if not force and not suffix and not _stale():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + suffix)
     os.makedirs(objdir, exist_ok=True)
     env = dict(os.environ)
     # the image's CC/CXX wrappers are not a supported nvcc host compiler setup; use the system g++
@@ -54,7 +56,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, "-ccbin", ccbin, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, "-ccbin", ccbin, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, src),
+               "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         log = r.stdout + r.stderr
         with open(os.path.join(objdir, src + ".ptxas.log"), "w") as f:
@@ -67,11 +70,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-ccbin", ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    cmd = [nvcc, "-ccbin", ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -1,0 +1,60 @@
+"""Drop-in for the reference's ``rne.py`` public surface, backed by libtcmp.so.
+
+Reference contract kept (rne.py:173-198): ``rne(q, qd, qdd) -> np.ndarray(7)``,
+``add_payload(r, m)``, ``remove_payload()``, ``get_has_payload()``, with the payload held in module
+state between calls exactly as the reference's closures expect (panda_primitives.py:178-190).
+``add_payload`` ignores ``r`` and attaches the payload iff ``m > 0`` like the reference (rne.py:181-188).
+
+New: ``rne_batch`` evaluates many states per call ([7][n] arrays, CUDA tensors or NumPy) and takes
+the payload as an argument instead of module state, so it is re-entrant.
+
+Every call runs on the GPU; a scalar ``rne()`` is a batch of one.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine
+from ._lib import PAYLOAD_THRESHOLD_RAW
+
+_has_payload = False
+_payload_mass = 0.0
+
+
+def get_has_payload() -> bool:
+    return _has_payload
+
+
+def set_has_payload(val: bool) -> None:
+    global _has_payload
+    _has_payload = bool(val)
+
+
+def add_payload(r, m) -> None:
+    """rne.py:181-188: replaces any previous payload; only ``m > 0`` attaches one; ``r`` is unused."""
+    global _has_payload, _payload_mass
+    remove_payload()
+    if m > 0:
+        _has_payload = True
+        _payload_mass = float(m)
+
+
+def remove_payload() -> None:
+    global _has_payload, _payload_mass
+    _has_payload = False
+    _payload_mass = 0.0
+
+
+def rne(q, qd, qdd) -> np.ndarray:
+    """Joint torques (7,) of the Panda + hand (+ current payload) -- rne.py:198-254."""
+    col = lambda v: np.asarray(v, dtype=np.float64).reshape(-1)[:7].reshape(7, 1)
+    tau, _ = engine.torque_test_batch(col(q), col(qd), col(qdd), _payload_mass if _has_payload else 0.0,
+                                      mode="rne", payload_threshold=PAYLOAD_THRESHOLD_RAW, want_mask=False)
+    return tau[:, 0].copy()
+
+
+def rne_batch(q, qd=None, qdd=None, payload_mass=0.0, dtype="f64"):
+    """Torques [7][n] for states [7][n]; payload attached iff mass > 0 (the raw rne.py rule)."""
+    tau, _ = engine.torque_test_batch(q, qd, qdd, payload_mass, mode="rne", dtype=dtype,
+                                      payload_threshold=PAYLOAD_THRESHOLD_RAW, want_mask=False)
+    return tau
