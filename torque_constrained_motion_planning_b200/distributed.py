@@ -1,0 +1,117 @@
+"""Multi-GPU sharding of the hot path: one process per GPU (torchrun), ``torch.distributed`` for plumbing.
+
+The units of every BASELINE config are independent (states, edges, (pose, free) solves), so they
+shard as contiguous equal blocks ``[r*n/G, (r+1)*n/G)`` per rank with NO collective on the data path.
+The only exchange is afterwards and tiny: an all-gather of the feasibility masks / first-failure
+indices (1 B or 4 B per unit) and, for IK, of the solution counts and solution sets -- NCCL over
+NVLink/NVSwitch on GPUs, gloo in the CPU tests.  The per-rank compute function is injectable so the
+host logic (bounds, padding, gather order) is testable on CPU with world_size 2.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous block of rank ``rank``: [lo, hi).  Blocks differ in size by at most one unit."""
+    lo = (n * rank) // world
+    hi = (n * (rank + 1)) // world
+    return lo, hi
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def _world(group=None):
+    dist = _dist()
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def all_gather_ragged(local, n_total: int, group=None):
+    """Gather per-rank blocks (first dim = units of this rank, sizes from shard_bounds) into the full
+    array on every rank.  Blocks are padded to the largest block so a single all_gather_into_tensor
+    (NCCL: one NVSwitch collective) moves them."""
+    import torch
+    dist = _dist()
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    sizes = [shard_bounds(n_total, r, world)[1] - shard_bounds(n_total, r, world)[0] for r in range(world)]
+    mx = max(sizes)
+    pad_shape = (mx,) + tuple(local.shape[1:])
+    padded = torch.zeros(pad_shape, dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    out = torch.empty((world,) + pad_shape, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out.view(world * mx, *local.shape[1:]), padded, group=group)
+    return torch.cat([out[r, : sizes[r]] for r in range(world)], dim=0)
+
+
+def sharded_torque_test(q, qd=None, qdd=None, payload_mass=0.0, mode="rne", group=None, gather=True,
+                        compute: Optional[Callable] = None, **kw):
+    """Every rank holds (or can index) the full SoA arrays ``[7][n]``; it evaluates only its block and, if
+    ``gather``, all ranks end up with the full feasibility mask ``[n]``.  Returns (mask, (lo, hi))."""
+    import torch
+    if compute is None:
+        from . import engine
+        compute = engine.torque_test_batch
+    rank, world = _world(group)
+    n = int(q.shape[1])
+    lo, hi = shard_bounds(n, rank, world)
+    sl = lambda a: None if a is None else a[:, lo:hi].contiguous() if hasattr(a, "contiguous") else np.ascontiguousarray(a[:, lo:hi])
+    pm = payload_mass if np.ndim(payload_mass) == 0 else payload_mass[lo:hi]
+    _, ok = compute(sl(q), sl(qd), sl(qdd), pm, mode=mode, want_tau=False, **kw)
+    if not gather or world == 1:
+        return ok, (lo, hi)
+    if not torch.is_tensor(ok):
+        ok = torch.as_tensor(ok)
+    return all_gather_ragged(ok, n, group), (lo, hi)
+
+
+def sharded_edge_feasibility(qa, qb, n_waypoints=64, payload_mass=0.0, mode="rne", group=None, gather=True,
+                             compute: Optional[Callable] = None, **kw):
+    """Edges shard by contiguous blocks; an edge never straddles ranks, so the per-edge first-failure
+    reduction needs no cross-GPU step.  Returns (first_fail [n_edges] on every rank, (lo, hi))."""
+    import torch
+    if compute is None:
+        from . import engine
+        compute = engine.edge_feasibility
+    rank, world = _world(group)
+    n = int(qa.shape[1])
+    lo, hi = shard_bounds(n, rank, world)
+    cut = lambda a: a[:, lo:hi].contiguous() if hasattr(a, "contiguous") else np.ascontiguousarray(a[:, lo:hi])
+    ff = compute(cut(qa), cut(qb), n_waypoints, payload_mass, mode=mode, **kw)
+    if not gather or world == 1:
+        return ff, (lo, hi)
+    if not torch.is_tensor(ff):
+        ff = torch.as_tensor(ff)
+    return all_gather_ragged(ff, n, group), (lo, hi)
+
+
+def sharded_ik(rot9, trans3, free, group=None, gather=True, compute: Optional[Callable] = None):
+    """Poses shard by contiguous blocks (each pose keeps its whole free-joint sweep on one rank).
+    Returns (sols [n*n_free][8][7], counts [n*n_free], (lo, hi)) gathered on every rank."""
+    import torch
+    if compute is None:
+        from . import engine
+        compute = lambda r, t, f: engine.ik_batch(r, t, f)[:2]
+    rank, world = _world(group)
+    n = int(rot9.shape[1])
+    lo, hi = shard_bounds(n, rank, world)
+    cut = lambda a: a[:, lo:hi].contiguous() if hasattr(a, "contiguous") else np.ascontiguousarray(a[:, lo:hi])
+    bcast = len(free.shape) == 1
+    n_free = int(free.shape[0])
+    sols, counts = compute(cut(rot9), cut(trans3), free if bcast else cut(free))
+    if not gather or world == 1:
+        return sols, counts, (lo, hi)
+    if not torch.is_tensor(sols):
+        sols, counts = torch.as_tensor(sols), torch.as_tensor(counts)
+    m = hi - lo
+    sols_g = all_gather_ragged(sols.reshape(m, n_free * 56), n, group).reshape(n * n_free, 8, 7)
+    counts_g = all_gather_ragged(counts.reshape(m, n_free), n, group).reshape(n * n_free)
+    return sols_g, counts_g, (lo, hi)
