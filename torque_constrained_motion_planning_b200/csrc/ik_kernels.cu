@@ -15,246 +15,11 @@
 // tests; ikfast_panda_arm.cpp:109-126), the clamped asin/acos (:136-142,169-175), the truncated
 // pi literals used for angle wrapping (:67-69) and the solver's numeric coefficients of the
 // Panda geometry.  One thread owns one (pose, free value) solve; up to 8 solutions.
-#include "panda_model.cuh"
+#include "ik_core.cuh"
 #include "tcmp_internal.h"
 
 namespace tcmp {
 namespace ik {
-
-constexpr double kPi = 3.14159265358979;      // IKPI   (ikfast_panda_arm.cpp:68) -- truncated on purpose
-constexpr double k2Pi = 6.28318530717959;     // IK2PI  (:67)
-constexpr double kPi2 = 1.57079632679490;     // IKPI_2 (:69)
-constexpr double kHalfPiLit = 1.5707963267949;  // literal the generated formulas use for pi/2
-constexpr double kSinCosThresh = 1e-7;        // IKFAST_SINCOS_THRESH   (:110)
-constexpr double kAtan2Thresh = 1e-7;         // IKFAST_ATAN2_MAGTHRESH (:115)
-constexpr double kSolutionThresh = 1e-6;      // IKFAST_SOLUTION_THRESH (:120)
-constexpr double kEvalThresh = 1e-5;          // IKFAST_EVALCOND_THRESH (:125)
-constexpr double kBranchThresh = 1e-6;        // "< 0.0000010000000000" tests on j*eval
-constexpr double kAngleThresh = 5e-6;         // "< 0.0000050000000000" tests on special angles
-
-__device__ __forceinline__ double clamp_asin(double f) {  // IKasin (:136-142)
-    if (f <= -1) return -kPi2;
-    if (f >= 1) return kPi2;
-    return asin(f);
-}
-__device__ __forceinline__ double clamp_acos(double f) {  // IKacos (:169-175)
-    if (f <= -1) return kPi;
-    if (f >= 1) return 0.0;
-    return acos(f);
-}
-__device__ __forceinline__ bool in_unit(double f) {  // the range guard in front of IKasin / IKacos
-    return !(f < -1 - kSinCosThresh || f > 1 + kSinCosThresh);
-}
-__device__ __forceinline__ double sign_of(double f) { return f > 0 ? 1.0 : (f < 0 ? -1.0 : 0.0); }  // IKsign
-__device__ __forceinline__ double wrap_pi(double a) {  // the "> IKPI -= IK2PI / < -IKPI += IK2PI" idiom
-    if (a > kPi) return a - k2Pi;
-    if (a < -kPi) return a + k2Pi;
-    return a;
-}
-// IKatan2WithCheck (:219-231): valid iff neither is NaN and |y| >= 1e-7 or |x| > 1e-7.
-__device__ __forceinline__ bool atan2_checked(double y, double x, double *out) {
-    if (isnan(y) || isnan(x)) return false;
-    if (!(fabs(y) >= kAtan2Thresh || fabs(x) > kAtan2Thresh)) return false;
-    *out = atan2(y, x);
-    return true;
-}
-
-struct Root {
-    double a, s, c;  // wrapped angle; sin/cos of the unwrapped angle, as the solver computes them
-};
-__device__ __forceinline__ Root make_root(double angle) {
-    Root r;
-    sincos(angle, &r.s, &r.c);
-    r.a = wrap_pi(angle);
-    return r;
-}
-__device__ __forceinline__ bool same_root(const Root &x, const Root &y) {  // duplicate-root test (:495)
-    return fabs(x.c - y.c) < kSolutionThresh && fabs(x.s - y.s) < kSolutionThresh;
-}
-
-struct Pose {
-    double r[3][3];
-    double px, py, pz;        // wrist centre: eetrans - 0.107 R[:,2] - (0,0,0.333)   (:431-439)
-    double pp, npx, npy, npz; // |p|^2 and R^T p                                      (:444-447)
-    double j6, s6, c6;
-};
-
-struct Emit {
-    double *sols;   // [8][7] or nullptr
-    int count;
-    unsigned status;
-};
-
-enum : unsigned { kStatusDegenerate = 1u };
-
-__device__ __forceinline__ void emit_solution(Emit &out, double j0, double j1, double j2, double j3, double j4,
-                                              double j5, double j6) {
-    if (out.sols && out.count < 8) {
-        double *s = out.sols + out.count * 7;
-        s[0] = j0; s[1] = j1; s[2] = j2; s[3] = j3; s[4] = j4; s[5] = j5; s[6] = j6;
-    }
-    ++out.count;
-}
-
-// Residual ZYZ problem (rotationfunction0, :3115): with j3,j4,j5,j6 fixed, M = R_{3..6}^T R must
-// equal Rz(j0) Ry(j1) Rz(j2).
-__device__ void solve_shoulder(const Pose &P, const Root &j3, const Root &j4, const Root &j5, Emit &out) {
-    // M = (Rz(j3') ...)^T R, written as three successive frame changes of the columns of R
-    // (:3122-3147): first about the tool axis by j6, then j5, j4, j3.
-    double M[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double ri0 = P.r[i][0], ri1 = P.r[i][1], ri2 = P.r[i][2];
-        const double a = P.c6 * ri0 - P.s6 * ri1;    // x122..x124
-        const double b = -P.s6 * ri0 - P.c6 * ri1;   // x126..x128
-        const double d = ri2 * j5.s + j5.c * a;      // x129..x131
-        const double e = j5.s * a - ri2 * j5.c;      // x125 - r*cj5, x134, x132
-        const double f = j4.c * d - j4.s * b;        // x133 + x120*x126, x135, x136
-        M[i][0] = j3.c * f - j3.s * e;
-        M[i][1] = j4.s * d + j4.c * b;
-        M[i][2] = j3.c * e + j3.s * f;
-    }
-    // j1 = +-acos(M22)  (:3149-3167)
-    Root j1r[2];
-    bool j1ok[2] = {false, false};
-    const double cj1 = M[2][2];
-    if (cj1 >= -1 - kSinCosThresh && cj1 <= 1 + kSinCosThresh) {
-        const double a = clamp_acos(cj1);
-        const double s = sin(a);
-        j1r[0] = {a, s, cj1};
-        j1r[1] = {-a, -s, cj1};
-        j1ok[0] = j1ok[1] = true;
-    } else if (isnan(cj1)) {
-        j1r[0] = {0.0, 0.0, 1.0};
-        j1ok[0] = true;
-    }
-    if (j1ok[0] && j1ok[1] && same_root(j1r[0], j1r[1])) j1ok[1] = false;
-
-    for (int i1 = 0; i1 < 2; ++i1) {
-        if (!j1ok[i1]) continue;
-        const double j1 = j1r[i1].a, s1 = j1r[i1].s, c1 = j1r[i1].c;
-        const double sg = sign_of(s1);
-        // general branch requires sin(j1) away from 0 and a usable (M12, M02) pair (:3185-3189)
-        if (fabs(s1) < kBranchThresh || fabs(M[1][2]) + fabs(M[0][2]) < kBranchThresh || fabs(sg) < kBranchThresh) {
-            out.status |= kStatusDegenerate;   // shoulder singularity: j0 / j2 axes aligned
-            continue;
-        }
-        double at;
-        if (!atan2_checked(M[1][2], M[0][2], &at)) continue;
-        const Root j0 = make_root(-kHalfPiLit + kHalfPiLit * (1.0 / sg) + at);  // (:9544-9552)
-        {
-            // 8 residuals (:9586-9593): column 2 of M against Rz(j0) Ry(j1)
-            const double a = M[0][2], b = M[1][2];
-            const double x02 = a * j0.c + b * j0.s;              // (Rz^T M)_02
-            const double x00 = M[0][0] * j0.c + M[1][0] * j0.s;  // (Rz^T M)_00
-            const double x01 = M[0][1] * j0.c + M[1][1] * j0.s;  // (Rz^T M)_01
-            const double e0 = a - j0.c * s1, e1 = b - j0.s * s1, e2 = b * j0.c - a * j0.s, e3 = x02 - s1;
-            const double e4 = c1 * x02 - s1 * M[2][2];
-            const double e5 = -(c1 * M[2][0] + s1 * x00), e6 = -(c1 * M[2][1] + s1 * x01);
-            const double e7 = 1.0 - c1 * M[2][2] - s1 * x02;
-            if (fabs(e0) > kEvalThresh || fabs(e1) > kEvalThresh || fabs(e2) > kEvalThresh || fabs(e3) > kEvalThresh ||
-                fabs(e4) > kEvalThresh || fabs(e5) > kEvalThresh || fabs(e6) > kEvalThresh || fabs(e7) > kEvalThresh)
-                continue;
-        }
-        if (fabs(M[2][0]) + fabs(M[2][1]) < kBranchThresh) {  // (:9601-9605); sin(j1) already tested
-            out.status |= kStatusDegenerate;
-            continue;
-        }
-        if (!atan2_checked(M[2][1], -M[2][0], &at)) continue;
-        const Root j2 = make_root(-kHalfPiLit + kHalfPiLit * (1.0 / sg) + at);  // (:12473-12481)
-        {
-            // 12 residuals (:12520-12531): M against Rz(j0) Ry(j1) Rz(j2), in three frames
-            const double c0 = j0.c, s0 = j0.s, c2 = j2.c, s2 = j2.s;
-            const double x00 = c0 * M[0][0] + s0 * M[1][0], x01 = c0 * M[0][1] + s0 * M[1][1];
-            const double y10 = c0 * M[1][0] - s0 * M[0][0], y11 = c0 * M[1][1] - s0 * M[0][1];
-            const double e[12] = {
-                s1 * c2 + M[2][0],
-                M[2][1] - s2 * s1,
-                x01 + c1 * s2,
-                y10 - s2,
-                y11 - c2,
-                s0 * c2 + M[0][1] + s2 * c0 * c1,
-                x00 - c1 * c2,
-                s0 * s2 + M[0][0] - c0 * c1 * c2,
-                s0 * c1 * s2 - c0 * c2 + M[1][1],
-                M[1][0] - c0 * s2 - c1 * c2 * s0,
-                c1 * x01 - M[2][1] * s1 + s2,
-                c1 * x00 - M[2][0] * s1 - c2,
-            };
-            bool bad = false;
-#pragma unroll
-            for (int t = 0; t < 12; ++t) bad = bad || (fabs(e[t]) > kEvalThresh);
-            if (bad) continue;
-        }
-        emit_solution(out, j0.a, j1, j2.a, j3.a, j4.a, j5.a, P.j6);
-    }
-}
-
-// One solve (IKSolver::ComputeIk, :412).
-__device__ void solve_one(const Pose &P, Emit &out) {
-    const double cn = P.c6 * P.npx;  // x78
-    const double sn = P.npy * P.s6;  // x79
-    // j3 from |p|^2 (:461-485)
-    const double arg3 = 0.986881610513004 + (-3.89793688895078) * P.pp + 0.686036892455338 * cn +
-                        (-0.686036892455338) * sn;
-    if (!in_unit(arg3)) return;
-    const double a3 = clamp_asin(arg3);
-    Root j3r[2] = {make_root(1.10379390314189 + a3), make_root(4.24538655673168 - a3)};
-    bool j3ok[2] = {true, !same_root(j3r[0], j3r[1])};
-
-    for (int i3 = 0; i3 < 2; ++i3) {
-        if (!j3ok[i3]) continue;
-        const Root &j3 = j3r[i3];
-        // branch guards for the j5 formula (:503-508)
-        const double g0 = 1.0 + 129.132231404959 * (cn * cn) + 22.7272727272727 * sn + 129.132231404959 * (sn * sn) +
-                          (-258.264462809917) * cn * sn + 129.132231404959 * (P.npz * P.npz) +
-                          (-22.7272727272727) * cn;
-        const double x975 = 0.088 - cn + sn;
-        const double g1 = fabs(x975) + fabs(P.npz);
-        if (fabs(g0) < kBranchThresh || fabs(g1) < kBranchThresh) {
-            out.status |= kStatusDegenerate;   // wrist centre on the joint-6 axis
-            continue;
-        }
-        // j5: two roots (:2347-2386)
-        double at5;
-        if (!atan2_checked(P.npz, x975, &at5)) continue;
-        const double h2 = x975 * x975 + P.npz * P.npz;
-        if (h2 < -0.00001) continue;
-        const double h = fabs(h2 <= 0.0 ? 0.0 : sqrt(h2));   // IKabs(IKsqrt(.)) (:183)
-        if (h == 0.0) continue;                              // IKPowWithIntegerCheck(.,-1) (:269)
-        const double arg5 = (1.0 / h) * (0.384 + (-0.0825) * j3.s + 0.316 * j3.c);
-        if (!in_unit(arg5)) continue;
-        const double a5 = clamp_asin(arg5);
-        Root j5r[2] = {make_root(-a5 - at5), make_root(3.14159265358979 + a5 - at5)};
-        bool j5ok[2] = {true, !same_root(j5r[0], j5r[1])};
-
-        for (int i5 = 0; i5 < 2; ++i5) {
-            if (!j5ok[i5]) continue;
-            const Root &j5 = j5r[i5];
-            // j4: one root (:2404-2408 guards, :3037-3045 formula)
-            const double K = -0.0825 + 0.0825 * j3.c + 0.316 * j3.s;
-            const double U = P.c6 * P.npy + P.npx * P.s6;
-            const double W = (-0.088) * j5.c - j5.c * sn + P.npz * j5.s + j5.c * cn;
-            const double q0 = -1.0 + j3.c + 3.83030303030303 * j3.s;
-            const double sK = sign_of(K);
-            if (fabs(q0) < kBranchThresh || fabs(U) + fabs(W) < kBranchThresh || fabs(sK) < kBranchThresh) {
-                out.status |= kStatusDegenerate;   // elbow offset cancels / j4 axis through the wrist
-                continue;
-            }
-            double at4;
-            if (!atan2_checked(U, W, &at4)) continue;
-            const Root j4 = make_root(-kHalfPiLit + at4 + kHalfPiLit * (1.0 / sK));
-            {
-                // 4 residuals (:3087-3090)
-                const double e0 = j4.s * K - U, e1 = j4.c * K - W, e2 = j4.c * U - j4.s * W,
-                             e3 = K - j4.c * W - j4.s * U;
-                if (fabs(e0) > kEvalThresh || fabs(e1) > kEvalThresh || fabs(e2) > kEvalThresh || fabs(e3) > kEvalThresh)
-                    continue;
-            }
-            solve_shoulder(P, j3, j4, j5, out);
-        }
-    }
-}
 
 __global__ void __launch_bounds__(128)
 ik_kernel(int64_t n, int n_free, int free_broadcast, const double *__restrict__ rot9,
@@ -267,21 +32,12 @@ ik_kernel(int64_t n, int n_free, int free_broadcast, const double *__restrict__ 
         // pose loads coalesce; the OUTPUT index stays pose*n_free + f as the ABI states.
         const int f = (int)(s / n);
         const int64_t p = s - (int64_t)f * n;
+        double R[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = __ldg(rot9 + i * n + p);
+        const double j6 = free_broadcast ? __ldg(free_vals + f) : __ldg(free_vals + (int64_t)f * n + p);
         Pose P;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) P.r[i][j] = __ldg(rot9 + (i * 3 + j) * n + p);
-        const double tx = __ldg(trans3 + p), ty = __ldg(trans3 + n + p), tz = __ldg(trans3 + 2 * n + p);
-        P.j6 = free_broadcast ? __ldg(free_vals + f) : __ldg(free_vals + (int64_t)f * n + p);
-        sincos(P.j6, &P.s6, &P.c6);
-        P.px = tx + (-0.107) * P.r[0][2];
-        P.py = (-0.107) * P.r[1][2] + ty;
-        P.pz = -0.333 + tz + (-0.107) * P.r[2][2];
-        P.pp = P.px * P.px + P.py * P.py + P.pz * P.pz;
-        P.npx = P.px * P.r[0][0] + P.py * P.r[1][0] + P.pz * P.r[2][0];
-        P.npy = P.px * P.r[0][1] + P.py * P.r[1][1] + P.pz * P.r[2][1];
-        P.npz = P.px * P.r[0][2] + P.py * P.r[1][2] + P.pz * P.r[2][2];
+        prepare_pose(R, __ldg(trans3 + p), __ldg(trans3 + n + p), __ldg(trans3 + 2 * n + p), j6, P);
 
         const int64_t o = p * n_free + f;
         Emit out;
