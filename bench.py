@@ -64,7 +64,8 @@ def workload_config(n_gpus):
         "l2": "inputs rotate over %d distinct 1M-state sets (%d MB) > 126 MB L2; no explicit flush"
               % (N_SETS, N_SETS * 176),
         "sharding": "states sharded across %d rank(s), no data-path collective; NCCL all-gather of the "
-                    "feasibility masks per step inside the timed region when N > 1" % n_gpus,
+                    "feasibility masks per step inside the timed region when N > 1 (side stream, overlapping "
+                    "the next step's kernel; joined before the stop event)" % n_gpus,
     }
 
 
@@ -130,8 +131,11 @@ def measured_peaks():
 
 
 def cpu_baseline_run(n_sample, reps, nthreads=0):
-    """C oracle port of rne.py + the limit compare, OpenMP over states, on a bounded sample."""
+    """C oracle port of rne.py + the limit compare, OpenMP over states, on a bounded sample.
+    nthreads = 0 -> every core this process may run on (torchrun exports OMP_NUM_THREADS=1; ignore it)."""
     import oracle
+    if nthreads == 0:
+        nthreads = len(os.sched_getaffinity(0))
     q, qd, qdd, mass = sample_states(n_sample, seed=2)
     oracle.torque_test_batch("rne", q[:, :1000], qd[:, :1000], qdd[:, :1000], mass[:1000], nthreads=nthreads)
     t0 = time.perf_counter()
@@ -140,6 +144,56 @@ def cpu_baseline_run(n_sample, reps, nthreads=0):
     dt = time.perf_counter() - t0
     cores = oracle.num_threads() if nthreads == 0 else nthreads
     return n_sample * reps / dt, cores, dt
+
+
+def run_extras(engine, dev, K):
+    """IK solves/s (config 3: 1M reachable poses x 25 free values) and RRT* edge checks/s (config 4: 100k edges
+    x 64 min-jerk waypoints, rne, 5 kg), device-resident, CUDA-event timed."""
+    import torch
+    out = {}
+    rng = np.random.default_rng(3)
+    n, n_free = 1_000_000, 25
+    q = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, n))
+    free = np.empty((n_free, n))
+    free[0] = q[6]
+    free[1:] = rng.uniform(-2.8973, 2.8973, size=(n_free - 1, n))
+    qd_, fd = torch.as_tensor(q, device=dev), torch.as_tensor(free, device=dev)
+
+    def timeit(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    t_fk = timeit(lambda: engine.fk_batch(qd_), 5)
+    trans, rot = engine.fk_batch(qd_)
+    t_cnt = timeit(lambda: engine.ik_batch(rot, trans, fd, want_sols=False, want_status=False), 3)
+    ns = 200_000   # with the [8][7] solution sets written (448 B/solve): 5M solves = 2.2 GB of output
+    t_sol = timeit(lambda: engine.ik_batch(rot[:, :ns].contiguous(), trans[:, :ns].contiguous(),
+                                           fd[:, :ns].contiguous(), want_status=False), 3)
+    _, counts, _ = engine.ik_batch(rot, trans, fd, want_sols=False, want_status=False)
+    hist = torch.bincount(counts.flatten().long(), minlength=9).tolist()
+    out["ik"] = {"workload": "configs[2]: 1M reachable poses x 25 free-joint values", "solves": n * n_free,
+                 "solves_per_s_counts_only": n * n_free / t_cnt, "solves_per_s_with_solutions": ns * n_free / t_sol,
+                 "fk_poses_per_s": n / t_fk, "count_histogram": hist}
+    E, W = 100_000, 64
+    rng = np.random.default_rng(4)
+    qa = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, E))
+    qb = np.clip(qa + rng.normal(0.0, 0.5, size=(7, E)), Q_LO[:, None], Q_HI[:, None])
+    a, b = torch.as_tensor(qa, device=dev), torch.as_tensor(qb, device=dev)
+    t_e = timeit(lambda: engine.edge_feasibility(a, b, W, 5.0, mode="rne"), max(K, 5))
+    ff = engine.edge_feasibility(a, b, W, 5.0, mode="rne")
+    evaluated = int(torch.clamp(((ff + 32) // 32) * 32, max=W).sum().item())   # waypoints actually evaluated (32/round)
+    out["edges"] = {"workload": "configs[3]: 100k edges x 64 min-jerk waypoints, rne, 5 kg", "edges_per_s": E / t_e,
+                    "waypoint_states_per_s_nominal": E * W / t_e, "waypoint_states_evaluated": evaluated,
+                    "feasible_fraction": float((ff == W).float().mean().item()), "ms": t_e * 1e3}
+    return out
 
 
 def run_reference(args):
@@ -206,13 +260,14 @@ def main():
         q, qd, qdd, mass = sample_states(N_STATES, seed=2 + 1000 * rank + s)
         sets.append(tuple(torch.as_tensor(a, device=dev) for a in (q, qd, qdd, mass)))
     host0 = sample_states(N_STATES, seed=2 + 1000 * rank)
-    gathered = torch.empty((world, N_STATES), dtype=torch.uint8, device=dev) if world > 1 else None
+    from torque_constrained_motion_planning_b200.distributed import OverlappedGather
+    gather = OverlappedGather((N_STATES,), torch.uint8, dev) if world > 1 else None
 
     def step(i, mode="rne"):
         q, qd, qdd, mass = sets[i % N_SETS]
         tau, ok = engine.torque_test_batch(q, qd, qdd, mass, mode=mode)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, ok)
+            gather.submit(ok)      # NCCL all-gather of this step's mask on a side stream (overlaps step i+1)
         return tau, ok
 
     def timed(fn, k):
@@ -223,6 +278,8 @@ def main():
         e0.record()
         for i in range(k):
             fn(i)
+        if gather is not None:
+            gather.join()          # the timed region ends when the last mask all-gather has landed
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -248,6 +305,8 @@ def main():
             step(held + i)
         held += 200
         torch.cuda.synchronize()
+    if gather is not None:
+        gather.join()
     e1.record()
     torch.cuda.synchronize()
     sustained = world * N_STATES * held / (e0.elapsed_time(e1) * 1e-3)
@@ -268,6 +327,11 @@ def main():
     # mask-only rne (the planner's actual need: 177 B/state)
     ms = timed(lambda i: engine.torque_test_batch(*sets[i % N_SETS], mode="rne", want_tau=False), K)
     modes["rne_mask_only"] = world * N_STATES * K / (ms * 1e-3)
+
+    # ---- the other hot-path workloads (BASELINE.json configs[2], configs[3]); single-GPU runs only -------
+    extras = {}
+    if world == 1:
+        extras = run_extras(engine, dev, K)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host arrays, H2D + D2H inside) -------
     pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
@@ -310,7 +374,11 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload_config(world),
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                "frac": achieved_tf / (fp64_peak / 1e12), "traffic": None,
+                "frac": achieved_tf / (fp64_peak / 1e12),
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, from the ncu --set full
+                # capture in profiles/r01/ncu_full_rne_batch_kernel_raw.csv (168.0 MB read + 26.0 MB written at
+                # kernel end; the remaining dirty lines are still in the 126 MB L2) -- <= 233 MB algorithmic
+                "traffic": 194.0e6,
                 "peak_source": "tcmp_fp64_peak DFMA microbenchmark measured in this run (MEASURED_PEAKS.json "
                                "carries no FP64 entry; datasheet 37.2 TFLOP/s)",
                 "flops_per_state": FLOPS_PER_STATE, "kernel": "rne_batch_kernel<double,DYN,!TOOL,tau,mask>",
@@ -320,6 +388,7 @@ def main():
                         "peak_source": peak_src},
             },
             "modes": modes,
+            "extras": extras,
             "sustained": {"value": sustained, "unit": UNIT, "steps": held,
                           "note": "same step held back to back for >= 1.5 s (device-timed); clocks sampled over it"},
             "e2e": {"value": e2e_value, "unit": UNIT,
