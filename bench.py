@@ -64,8 +64,9 @@ def workload_config(n_gpus):
         "l2": "inputs rotate over %d distinct 1M-state sets (%d MB) > 126 MB L2; no explicit flush"
               % (N_SETS, N_SETS * 176),
         "sharding": "states sharded across %d rank(s), no data-path collective; NCCL all-gather of the "
-                    "feasibility masks per step inside the timed region when N > 1 (side stream, overlapping "
-                    "the next step's kernel; joined before the stop event)" % n_gpus,
+                    "feasibility masks per step inside the timed region when N > 1: fused into the kernel as "
+                    "NVLink peer stores (tcmp_rne_batch_scatter, checked against NCCL all_gather), or "
+                    "--gather nccl = NCCL all_gather_into_tensor on a side stream" % n_gpus,
     }
 
 
@@ -234,6 +235,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the feasibility masks are all-gathered each step: p2p = peer stores fused into "
+                         "the torque kernel (tcmp_rne_batch_scatter); nccl = all_gather_into_tensor on a side stream")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -260,13 +264,21 @@ def main():
         q, qd, qdd, mass = sample_states(N_STATES, seed=2 + 1000 * rank + s)
         sets.append(tuple(torch.as_tensor(a, device=dev) for a in (q, qd, qdd, mass)))
     host0 = sample_states(N_STATES, seed=2 + 1000 * rank)
-    from torque_constrained_motion_planning_b200.distributed import OverlappedGather
-    gather = OverlappedGather((N_STATES,), torch.uint8, dev) if world > 1 else None
+    from torque_constrained_motion_planning_b200.distributed import OverlappedGather, PeerMaskBuffer
+    gather = None
+    peer = None
+    if world > 1 and args.gather == "nccl":
+        gather = OverlappedGather((N_STATES,), torch.uint8, dev)
+    elif world > 1:
+        peer = PeerMaskBuffer(N_STATES)   # gathered [world][N_STATES] mask buffer, written by every rank's kernel
 
     def step(i, mode="rne"):
         q, qd, qdd, mass = sets[i % N_SETS]
+        if peer is not None:
+            # fused compute + all-gather: the kernel stores each mask byte into every rank's gathered buffer
+            return peer.torque_test(q, qd, qdd, mass, mode=mode), None
         tau, ok = engine.torque_test_batch(q, qd, qdd, mass, mode=mode)
-        if world > 1:
+        if gather is not None:
             gather.submit(ok)      # NCCL all-gather of this step's mask on a side stream (overlaps step i+1)
         return tau, ok
 
@@ -327,6 +339,15 @@ def main():
     # mask-only rne (the planner's actual need: 177 B/state)
     ms = timed(lambda i: engine.torque_test_batch(*sets[i % N_SETS], mode="rne", want_tau=False), K)
     modes["rne_mask_only"] = world * N_STATES * K / (ms * 1e-3)
+    if peer is not None:
+        # correctness of the fused gather: every rank must now hold every rank's mask of the last step
+        last = (K - 1) % N_SETS
+        step(last)
+        peer.barrier()
+        mine = engine.torque_test_batch(*sets[last], mode="rne", want_tau=False)[1]
+        ref = torch.empty((world, N_STATES), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(ref, mine)
+        assert torch.equal(ref, peer.gathered), "peer-store gather != NCCL all-gather"
 
     # ---- the other hot-path workloads (BASELINE.json configs[2], configs[3]); single-GPU runs only -------
     extras = {}

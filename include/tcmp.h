@@ -75,6 +75,26 @@ int tcmp_rne_batch(int mode, int dtype, int64_t n, const void *q, const void *qd
                    void *tau_out, uint8_t *feasible_out, void *stream);
 
 /*
+ * Multi-GPU form of tcmp_rne_batch: the feasibility byte of state i is stored into dest_masks[d][dest_offset + i]
+ * for every d < n_dest -- the gathered mask buffers of all ranks (this rank's own and its peers', mapped with
+ * tcmp_peer_open over NVLink/NVSwitch).  This is the "NCCL all-gather of the masks" of BASELINE.json's
+ * north_star fused into the producing kernel as a peer-store epilogue.  fp64 only.  Consumers on other ranks
+ * must order their reads after this kernel (stream sync + any cross-rank barrier).
+ */
+#define TCMP_MAX_PEERS 8
+int tcmp_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
+                           const void *payload_mass, double payload_scalar, double payload_threshold,
+                           void *tau_out, int n_dest, void *const *dest_masks, int64_t dest_offset,
+                           void *stream);
+/* Peer-shareable device memory (cudaMalloc + CUDA IPC): allocate on the current device and export a 64-byte
+ * handle; another process on the same node opens the handle to obtain a pointer valid on ITS current device. */
+#define TCMP_IPC_HANDLE_BYTES 64
+int tcmp_peer_alloc(void **dev_ptr, int64_t bytes, unsigned char *handle_out);
+int tcmp_peer_free(void *dev_ptr);
+int tcmp_peer_open(const unsigned char *handle, void **peer_ptr);
+int tcmp_peer_close(void *peer_ptr);
+
+/*
  * RRT* edge check: for every edge (qa -> qb) generate n_waypoints samples of the 2-point
  * min-jerk (min_jerk_v2.py:96-142 coefficients, :176-181 t = linspace(1/W, 1, W), :216-220
  * x/v/a) and run the torque test on each (q, qd, qdd); first_fail_out[e] = index of the first

@@ -1,9 +1,10 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.log 2>&1; echo "exit $?" >> gpurun_out/bench_n1.log; tail -3 gpurun_out/bench_n1.log
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k scatter 2>&1 | tail -3
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
     bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.log 2>&1; echo "exit $?" >> gpurun_out/bench_n2.log
 tail -3 gpurun_out/bench_n2.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 2 --steps 20 --warmup 5 --gather nccl --no-cpu-baseline > gpurun_out/bench_n2_nccl.log 2>&1; tail -2 gpurun_out/bench_n2_nccl.log
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 \
     bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_ref_n2.log 2>&1; tail -2 gpurun_out/bench_ref_n2.log

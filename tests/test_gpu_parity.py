@@ -292,3 +292,22 @@ def test_ik_round_trip_100k(eng):
     idx = torch.nonzero(valid)[:, 0] // 3                # pose index of each solution
     assert (t2 - trans[:, idx]).abs().max().item() < 1e-6
     assert (r2 - rot[:, idx]).abs().max().item() < 1e-6
+
+
+# ---- fused peer-store gather (single process: the only destination is this rank's own buffer) -----------
+def test_scatter_kernel_single_rank(eng):
+    import torch
+    from torque_constrained_motion_planning_b200.distributed import PeerMaskBuffer
+    n = 100_003
+    q, qd, qdd, mass = sample_states(n, seed=21)
+    buf = PeerMaskBuffer(n)
+    assert buf.world == 1 and buf.gathered.shape == (1, n)
+    for mode in ["rne", "nov", "dyn", "base"]:
+        buf.gathered.zero_()
+        tau = buf.torque_test(dev(q), dev(qd), dev(qdd), dev(mass), mode=mode)
+        buf.barrier()
+        tau_o, ok_o = oracle.torque_test_batch(mode, q, qd, qdd, mass)
+        assert np.array_equal(buf.gathered[0].cpu().numpy(), ok_o)
+        if mode != "base":
+            assert np.abs(tau.cpu().numpy() - tau_o).max() < TOL64
+    buf.close()

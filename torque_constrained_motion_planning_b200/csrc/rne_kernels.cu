@@ -12,11 +12,22 @@
 
 namespace tcmp {
 
-template <typename T, bool DYN, bool TOOL, bool WRITE_TAU, bool WRITE_MASK>
+// SCATTER: the fused "compute + all-gather" form for multi-GPU runs.  Instead of writing its mask shard
+// locally and letting a separate NCCL all-gather move it, every thread stores its mask byte straight into
+// the gathered buffer of EVERY rank (peer pointers mapped over NVLink/NVSwitch, CUDA IPC) at
+// dest_offset + i.  1 B/state/peer of NVLink traffic rides under an FP64-bound kernel; no extra launch,
+// no host-side collective call (which costs more CPU time than this 63 us kernel runs).
+struct MaskDests {
+    uint8_t *p[TCMP_MAX_PEERS];
+    int n;
+    int64_t offset;
+};
+
+template <typename T, bool DYN, bool TOOL, bool WRITE_TAU, bool WRITE_MASK, bool SCATTER = false>
 __global__ void __launch_bounds__(128)
 rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, const T *__restrict__ qdd,
                  const T *__restrict__ payload_mass, T payload_scalar, T payload_threshold,
-                 T *__restrict__ tau_out, uint8_t *__restrict__ feasible_out) {
+                 T *__restrict__ tau_out, uint8_t *__restrict__ feasible_out, MaskDests dests) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         T qs[7], vs[7], as[7], tau[7];
@@ -38,7 +49,14 @@ rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, c
 #pragma unroll
             for (int j = 0; j < 7; ++j) __stcs(tau_out + j * n + i, tau[j]);
         }
-        if constexpr (WRITE_MASK) __stcs(feasible_out + i, (uint8_t)within_limits<T>(tau));
+        if constexpr (SCATTER) {
+            const uint8_t m = (uint8_t)within_limits<T>(tau);
+#pragma unroll
+            for (int d = 0; d < TCMP_MAX_PEERS; ++d)   // unrolled: constant indices keep `dests` in param space
+                if (d < dests.n) dests.p[d][dests.offset + i] = m;
+        } else if constexpr (WRITE_MASK) {
+            __stcs(feasible_out + i, (uint8_t)within_limits<T>(tau));
+        }
     }
 }
 
@@ -48,7 +66,7 @@ static cudaError_t launch_one(int64_t n, const void *q, const void *qd, const vo
     auto kern = rne_batch_kernel<T, DYN, TOOL, WT, WM>;
     const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, n);
     kern<<<grid, 128, 0, st>>>(n, (const T *)q, (const T *)qd, (const T *)qdd, (const T *)pm, (T)ps, (T)pt,
-                               (T *)tau, mask);
+                               (T *)tau, mask, MaskDests());
     return cudaGetLastError();
 }
 
@@ -89,6 +107,46 @@ cudaError_t launch_rne_batch(int mode, int dtype, int64_t n, const void *q, cons
     }
     if (dtype == TCMP_F64) return launch_typed<double>(mode, n, q, qd, qdd, pm, ps, pt, tau, mask, st);
     return launch_typed<float>(mode, n, q, qd, qdd, pm, ps, pt, tau, mask, st);
+}
+
+template <typename T, bool DYN, bool TOOL>
+static cudaError_t launch_scatter_t(int64_t n, const void *q, const void *qd, const void *qdd, const void *pm,
+                                    double ps, double pt, void *tau, const MaskDests &dests, cudaStream_t st) {
+    if (tau) {
+        auto kern = rne_batch_kernel<T, DYN, TOOL, true, true, true>;
+        const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, n);
+        kern<<<grid, 128, 0, st>>>(n, (const T *)q, (const T *)qd, (const T *)qdd, (const T *)pm, (T)ps, (T)pt,
+                                   (T *)tau, nullptr, dests);
+    } else {
+        auto kern = rne_batch_kernel<T, DYN, TOOL, false, true, true>;
+        const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, n);
+        kern<<<grid, 128, 0, st>>>(n, (const T *)q, (const T *)qd, (const T *)qdd, (const T *)pm, (T)ps, (T)pt,
+                                   (T *)tau, nullptr, dests);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
+                                     const void *pm, double ps, double pt, void *tau, int n_dest,
+                                     void *const *dest_masks, int64_t dest_offset, cudaStream_t st) {
+    MaskDests d;
+    d.n = n_dest;
+    d.offset = dest_offset;
+    for (int i = 0; i < TCMP_MAX_PEERS; ++i) d.p[i] = i < n_dest ? (uint8_t *)dest_masks[i] : nullptr;
+    if (dtype != TCMP_F64) return cudaErrorNotSupported;
+    const bool dynamic = (mode != TCMP_MODE_NOV) && qd && qdd;
+    const bool tool = (mode == TCMP_MODE_DYN);
+    if (mode == TCMP_MODE_BASE) {
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < n_dest && e == cudaSuccess; ++i) e = launch_fill<uint8_t>(n, d.p[i] + dest_offset, 1, st);
+        return e;
+    }
+    if (dynamic) {
+        if (tool) return launch_scatter_t<double, true, true>(n, q, qd, qdd, pm, ps, pt, tau, d, st);
+        return launch_scatter_t<double, true, false>(n, q, qd, qdd, pm, ps, pt, tau, d, st);
+    }
+    if (tool) return launch_scatter_t<double, false, true>(n, q, qd, qdd, pm, ps, pt, tau, d, st);
+    return launch_scatter_t<double, false, false>(n, q, qd, qdd, pm, ps, pt, tau, d, st);
 }
 
 }  // namespace tcmp

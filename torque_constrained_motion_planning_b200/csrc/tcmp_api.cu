@@ -139,6 +139,54 @@ int tcmp_rne_batch(int mode, int dtype, int64_t n, const void *q, const void *qd
     return TCMP_OK;
 }
 
+int tcmp_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
+                           const void *payload_mass, double payload_scalar, double payload_threshold, void *tau_out,
+                           int n_dest, void *const *dest_masks, int64_t dest_offset, void *stream) {
+    if (int rc = check_common(mode, dtype, n)) return rc;
+    if (dtype != TCMP_F64) return fail(TCMP_ERR_UNSUPPORTED, "scatter form is fp64 only");
+    if (n_dest < 1 || n_dest > TCMP_MAX_PEERS || !dest_masks || dest_offset < 0)
+        return fail(TCMP_ERR_INVALID_ARG, "bad destination list");
+    for (int i = 0; i < n_dest; ++i)
+        if (!dest_masks[i]) return fail(TCMP_ERR_INVALID_ARG, "dest_masks[%d] is NULL", i);
+    if (n == 0) return TCMP_OK;
+    if (!q && mode != TCMP_MODE_BASE) return fail(TCMP_ERR_INVALID_ARG, "q is NULL");
+    if ((qd == nullptr) != (qdd == nullptr))
+        return fail(TCMP_ERR_INVALID_ARG, "qd and qdd must both be given or both be NULL");
+    TCMP_CUDA(launch_rne_batch_scatter(mode, dtype, n, q, qd, qdd, payload_mass, payload_scalar, payload_threshold,
+                                       tau_out, n_dest, dest_masks, dest_offset, (cudaStream_t)stream));
+    return TCMP_OK;
+}
+
+int tcmp_peer_alloc(void **dev_ptr, int64_t bytes, unsigned char *handle_out) {
+    if (!dev_ptr || bytes <= 0 || !handle_out) return fail(TCMP_ERR_INVALID_ARG, "bad peer alloc");
+    static_assert(sizeof(cudaIpcMemHandle_t) == TCMP_IPC_HANDLE_BYTES, "IPC handle size");
+    TCMP_CUDA(cudaMalloc(dev_ptr, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*dev_ptr);
+        *dev_ptr = nullptr;
+        return cuda_fail(e, "cudaIpcGetMemHandle");
+    }
+    memcpy(handle_out, &h, sizeof(h));
+    return TCMP_OK;
+}
+int tcmp_peer_free(void *dev_ptr) {
+    if (dev_ptr) TCMP_CUDA(cudaFree(dev_ptr));
+    return TCMP_OK;
+}
+int tcmp_peer_open(const unsigned char *handle, void **peer_ptr) {
+    if (!handle || !peer_ptr) return fail(TCMP_ERR_INVALID_ARG, "bad peer open");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    TCMP_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TCMP_OK;
+}
+int tcmp_peer_close(void *peer_ptr) {
+    if (peer_ptr) TCMP_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return TCMP_OK;
+}
+
 int tcmp_edge_feasibility(int mode, int dtype, int64_t n_edges, int n_waypoints, const void *qa, const void *qb,
                           double payload_scalar, double payload_threshold, int static_only,
                           int32_t *first_fail_out, void *stream) {

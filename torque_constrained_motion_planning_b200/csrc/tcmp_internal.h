@@ -30,6 +30,11 @@ cudaError_t launch_rne_batch(int mode, int dtype, int64_t n, const void *q, cons
                              const void *payload_mass, double payload_scalar, double payload_threshold,
                              void *tau_out, uint8_t *feasible_out, cudaStream_t st);
 
+cudaError_t launch_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
+                                     const void *payload_mass, double payload_scalar, double payload_threshold,
+                                     void *tau_out, int n_dest, void *const *dest_masks, int64_t dest_offset,
+                                     cudaStream_t st);
+
 cudaError_t launch_edge_feasibility(int mode, int dtype, int64_t n_edges, int n_waypoints, const void *qa,
                                     const void *qb, double payload_scalar, double payload_threshold,
                                     int static_only, int32_t *first_fail_out, cudaStream_t st);

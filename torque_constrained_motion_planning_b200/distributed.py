@@ -146,3 +146,85 @@ class OverlappedGather:
     def join(self):
         self._torch.cuda.current_stream().wait_stream(self.stream)
         return self.out
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ holder so torch can view memory owned by libtcmp.so."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerMaskBuffer:
+    """Gathered feasibility-mask buffer ``[world][n_per_rank]`` that every rank's torque kernel writes into
+    DIRECTLY (tcmp_rne_batch_scatter): the all-gather of the masks fused into the producing kernel as a
+    peer-store epilogue over NVLink/NVSwitch.  Each rank allocates its copy with tcmp_peer_alloc (cudaMalloc +
+    CUDA IPC), the 64-byte handles are exchanged once through torch.distributed, and peers are mapped with
+    tcmp_peer_open.  After ``torque_test`` + a stream sync + ``barrier()`` every rank holds every mask."""
+
+    def __init__(self, n_per_rank: int, group=None):
+        import ctypes
+
+        import torch
+        from . import _lib
+        self._lib = _lib.load()
+        self._check = _lib.check
+        self.group = group
+        self.rank, self.world = _world(group)
+        if self.world > 8:
+            raise ValueError("at most 8 peers (one NVSwitch node)")
+        self.n = int(n_per_rank)
+        nbytes = self.n * self.world
+        self._own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        self._check(self._lib.tcmp_peer_alloc(ctypes.byref(self._own), nbytes, handle))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=dev)
+        if self.world > 1:
+            allh = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
+            _dist().all_gather_into_tensor(allh, mine, group=group)
+            allh = allh.cpu().numpy()
+        self._peers = []
+        ptrs = (ctypes.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs[r] = self._own.value
+            else:
+                p = ctypes.c_void_p()
+                self._check(self._lib.tcmp_peer_open(bytes(allh[r].tobytes()), ctypes.byref(p)))
+                self._peers.append(p)
+                ptrs[r] = p.value
+        self._ptrs = ptrs
+        self.gathered = torch.as_tensor(_DevArray(self._own.value, nbytes), device=dev).view(self.world, self.n)
+
+    def torque_test(self, q, qd=None, qdd=None, payload_mass=0.0, mode="rne", payload_threshold=0.01,
+                    want_tau=True):
+        """Evaluate this rank's block (q/qd/qdd [7][n] CUDA tensors) and store its mask into row ``rank`` of the
+        gathered buffer on EVERY rank.  Returns tau [7][n] (or None)."""
+        import torch
+        from ._lib import DTYPE, MODE
+        n = int(q.shape[1])
+        assert n <= self.n
+        scalar, pm = (float(payload_mass), None) if np.ndim(payload_mass) == 0 else (0.0, payload_mass)
+        tau = torch.empty((7, n), dtype=torch.float64, device=q.device) if want_tau else None
+        ptr = lambda t: None if t is None else int(t.data_ptr())
+        self._check(self._lib.tcmp_rne_batch_scatter(
+            MODE[mode], DTYPE["f64"], n, ptr(q), ptr(qd), ptr(qdd), ptr(pm), scalar, float(payload_threshold),
+            ptr(tau), self.world, self._ptrs, self.rank * self.n, int(torch.cuda.current_stream().cuda_stream)))
+        return tau
+
+    def barrier(self):
+        """Order every rank's peer stores before anyone reads ``gathered``."""
+        import torch
+        torch.cuda.synchronize()
+        if self.world > 1:
+            _dist().barrier(group=self.group)
+
+    def close(self):
+        for p in self._peers:
+            self._lib.tcmp_peer_close(p)
+        self._peers = []
+        if self._own:
+            self.gathered = None
+            self._lib.tcmp_peer_free(self._own)
+            self._own = None
