@@ -136,9 +136,54 @@ int tcmp_ik_batch(int64_t n, const double *rot9, const double *trans3, const dou
                   int n_free, int free_broadcast, double *sols_out, int32_t *count_out,
                   uint8_t *status_out, void *stream);
 
+/*
+ * Goal-IK selection: for every pose sweep the free joint (free_vals as in tcmp_ik_batch), solve, keep only
+ * solutions inside [q_lo, q_hi] (HOST arrays of 7; ikfast.py:167, franka_ik_fast.py:55-57) that pass the STATIC
+ * torque test `mode` with payload `payload_scalar` (panda_primitives.py:263; TCMP_MODE_BASE = no torque test), and
+ * return the one nearest to q_ref ([7][n], or [7] when ref_broadcast != 0) in the max norm (use_max_norm != 0,
+ * closest_inverse_kinematics ikfast.py:172-188) or the Euclidean norm (ik_utils.select_solution :43-52).
+ *   best_q [7][n], best_cost [n] (+inf when no solution survives), n_valid [n] = surviving solutions.
+ * Ties keep the first solution in (free value, solver order).
+ */
+int tcmp_ik_select(int64_t n, const double *rot9, const double *trans3, const double *free_vals, int n_free,
+                   int free_broadcast, const double *q_ref, int ref_broadcast, const double *q_lo_host,
+                   const double *q_hi_host, int mode, double payload_scalar, double payload_threshold,
+                   int use_max_norm, double *best_q, double *best_cost, int32_t *n_valid, void *stream);
+
 /* Batched FK, replaces ComputeFk (ikfast_panda_arm.cpp:307-395): q [7][n] -> trans3 [3][n],
  * rot9 [9][n] (row-major), link0 -> link8. */
 int tcmp_fk_batch(int64_t n, const double *q, double *trans3, double *rot9, void *stream);
+
+/*
+ * Synthetic-scene collision predicate (stand-in for utils.get_collision_fn, utils.py:3165-3218, whose PyBullet
+ * backend is out of scope): joint-limit test first (utils.py:3177-3178), then link spheres from the DH forward
+ * kinematics against axis-aligned boxes / spheres.  Obstacle and limit arrays are HOST memory (copied into the
+ * launch parameters).  hit_out[i] = 1 when configuration i collides or violates a joint limit.
+ */
+#define TCMP_MAX_OBSTACLES 32
+typedef struct {
+    int32_t kind;      /* 0 = axis-aligned box, 1 = sphere */
+    int32_t reserved;
+    double center[3];
+    double half[3];    /* box half extents; sphere: half[0] = radius */
+} tcmp_obstacle;
+int tcmp_collision_batch(int64_t n, const double *q, int n_obs, const tcmp_obstacle *obstacles_host,
+                         const double *q_lo_host, const double *q_hi_host, double payload_radius,
+                         uint8_t *hit_out, void *stream);
+/*
+ * RRT* tree-growth edge check, safe_path_force_aware(extend(q1, q2), collision, torque) (rrt_star.py:90-98,172) for
+ * MANY candidate edges in one launch.  The extend steps are generated on the device exactly as
+ * utils.get_extend_fn / get_refine_fn do (utils.py:3031-3041,3068-3077: floor(||(q2-q1)/resolution||_2) + 1
+ * configurations, q1 excluded, q2 included); each is tested for collision and, only if collision-free, with the
+ * STATIC torque test `mode` (tree growth never passes velocities, rrt_star.py:95).
+ *   q1, q2 [7][n_edges] (device); resolution_host [7];
+ *   n_steps_out[e] = number of configurations on edge e, prefix_out[e] = length of the safe prefix (0..n_steps).
+ */
+int tcmp_extend_prefix(int mode, int64_t n_edges, const double *q1, const double *q2,
+                       const double *resolution_host, int n_obs, const tcmp_obstacle *obstacles_host,
+                       const double *q_lo_host, const double *q_hi_host, double payload_radius,
+                       double payload_scalar, double payload_threshold, int32_t *n_steps_out,
+                       int32_t *prefix_out, void *stream);
 
 /*
  * Host-buffer variants: the call a Python/C caller makes with ordinary (ideally pinned) host

@@ -311,3 +311,86 @@ def test_scatter_kernel_single_rank(eng):
         if mode != "base":
             assert np.abs(tau.cpu().numpy() - tau_o).max() < TOL64
     buf.close()
+
+
+def test_ik_select_vs_composed_reference(eng):
+    """tcmp_ik_select == reference IK (compiled) -> joint-limit filter (ikfast.py:167) -> static torque test
+    (oracle) -> nearest to the current configuration (max norm, ikfast.py:172-188), composed on the CPU."""
+    from conftest import Q_HI, Q_LO
+    rng = np.random.default_rng(44)
+    n, nf = 3000, 6
+    q = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, n))
+    trans, rot = oracle.ref_fk_batch(q)
+    free = np.vstack([q[6:7], rng.uniform(Q_LO[6], Q_HI[6], size=(nf - 1, n))])
+    q_ref = np.clip(q + rng.normal(0, 0.4, size=q.shape), Q_LO[:, None], Q_HI[:, None])
+    sols, counts = oracle.ref_ik_batch(rot, trans, free)
+    for mode, mass, norm in [("rne", 5.0, "inf"), ("nov", 3.0, "l2"), ("base", 0.0, "inf"), ("dyn", 4.0, "inf")]:
+        best, cost, nv = eng.ik_select(rot, trans, free, q_ref, mass, mode=mode, norm=norm)
+        exp_cost = np.full(n, np.inf)
+        exp_best = np.zeros((7, n))
+        exp_nv = np.zeros(n, dtype=np.int32)
+        # flatten all candidate solutions, test them in one oracle call
+        cand, owner = [], []
+        for p in range(n):
+            for f in range(nf):
+                s = p * nf + f
+                for k in range(counts[s]):
+                    c = sols[s, k]
+                    if np.all(c >= Q_LO) and np.all(c <= Q_HI):
+                        cand.append(c); owner.append(p)
+        cand = np.array(cand); owner = np.array(owner)
+        _, ok = oracle.torque_test_batch(mode, np.ascontiguousarray(cand.T), None, None, mass)
+        for c, p, o in zip(cand, owner, ok):
+            if not o:
+                continue
+            exp_nv[p] += 1
+            d = np.abs(c - q_ref[:, p])
+            cst = d.max() if norm == "inf" else np.sqrt((d * d).sum())
+            if cst < exp_cost[p]:
+                exp_cost[p], exp_best[:, p] = cst, c
+        assert np.array_equal(nv, exp_nv), mode
+        fin = np.isfinite(exp_cost)
+        assert np.array_equal(np.isfinite(cost), fin)
+        assert np.abs(cost[fin] - exp_cost[fin]).max() < 1e-9
+        assert np.abs(best[:, fin] - exp_best[:, fin]).max() < 1e-9
+        assert fin.mean() > 0.3
+
+
+# ---- collision stand-in + fused tree-growth edge check (SURVEY 8f-1/8f-2) ---------------------------
+def test_collision_kernel_matches_numpy_stand_in(eng):
+    from conftest import Q_HI, Q_LO
+    from torque_constrained_motion_planning_b200 import collision
+    rng = np.random.default_rng(50)
+    qs = rng.uniform(Q_LO - 0.05, Q_HI + 0.05, size=(20_000, 7))       # a few outside the joint limits
+    for scene, pr in [(collision.hiro_scene(), 0.0), (collision.cluttered_scene(), 0.04), ([], 0.0)]:
+        ref = collision.get_collision_fn(obstacles=scene, payload_radius=pr).batch(qs)
+        hit = eng.collision_batch(np.ascontiguousarray(qs.T), scene, payload_radius=pr)
+        assert np.array_equal(hit.astype(bool), ref)
+        assert 0.02 < ref.mean() < 0.98
+
+
+def test_extend_prefix_matches_serial_safe_path(eng):
+    """One launch over many candidate edges == safe_path_force_aware(extend(q1, q2), collision, torque)
+    (rrt_star.py:90-98) edge by edge with the NumPy collision stand-in and the CPU oracle torque test."""
+    from conftest import Q_HI, Q_LO
+    from torque_constrained_motion_planning_b200 import collision, rrt_star, utils
+    rng = np.random.default_rng(51)
+    E = 400
+    q1 = rng.uniform(Q_LO, Q_HI, size=(E, 7))
+    q2 = np.clip(q1 + rng.normal(0, 0.8, size=(E, 7)), Q_LO - 0.02, Q_HI + 0.02)
+    q2[:20] = q1[:20]                                                    # zero-length edges: 1 configuration
+    res = 0.1 * np.ones(7)
+    scene = collision.cluttered_scene()
+    col = collision.get_collision_fn(obstacles=scene)
+    ext = utils.get_extend_fn(None, list(range(7)), resolutions=res)
+    for mode, mass in [("rne", 5.0), ("nov", 1.0), ("base", 0.0)]:
+        def tq(q, _mode=mode, _mass=mass):
+            _, ok = oracle.torque_test_batch(_mode, np.asarray(q, dtype=float).reshape(7, 1), None, None, _mass)
+            return bool(ok[0])
+        ns, pre = eng.extend_prefix(np.ascontiguousarray(q1.T), np.ascontiguousarray(q2.T), res, scene, mass, mode=mode)
+        for e in range(E):
+            seq = list(ext(tuple(q1[e]), tuple(q2[e])))
+            safe = rrt_star.safe_path_force_aware(seq, lambda q: col(q), tq)
+            assert ns[e] == len(seq), (e, ns[e], len(seq))
+            assert pre[e] == len(safe), (mode, e, pre[e], len(safe))
+        assert (pre < ns).mean() > 0.1 and (pre == ns).mean() > 0.1

@@ -38,6 +38,10 @@ SIGNATURES = {
     "tcmp_edge_feasibility": (_i32, [_i32, _i32, _i64, _i32, _vp, _vp, _f64, _f64, _i32, _vp, _vp]),
     "tcmp_traj_feasibility": (_i32, [_i32, _i32, _i32, _i32, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tcmp_ik_batch": (_i32, [_i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "tcmp_ik_select": (_i32, [_i64, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _f64, _f64, _i32, _vp, _vp,
+                              _vp, _vp]),
+    "tcmp_collision_batch": (_i32, [_i64, _vp, _i32, _vp, _vp, _vp, _f64, _vp, _vp]),
+    "tcmp_extend_prefix": (_i32, [_i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _f64, _f64, _f64, _vp, _vp, _vp]),
     "tcmp_fk_batch": (_i32, [_i64, _vp, _vp, _vp, _vp]),
     "tcmp_workspace_create": (_i32, [ctypes.POINTER(_vp), _i64]),
     "tcmp_workspace_destroy": (_i32, [_vp]),

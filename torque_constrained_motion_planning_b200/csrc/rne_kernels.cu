@@ -23,8 +23,18 @@ struct MaskDests {
     int64_t offset;
 };
 
+// Launch bounds: 128-thread CTAs; ptxas settles on 126 registers (4 CTAs / SM) with no spills.  Capping
+// lower (TCMP_RNE_MIN_BLOCKS=5) trades spills for occupancy -- measured slower, see profiles/.
+#ifndef TCMP_RNE_BLOCK
+#define TCMP_RNE_BLOCK 128
+#endif
+#ifdef TCMP_RNE_MIN_BLOCKS
+#define TCMP_RNE_BOUNDS TCMP_RNE_BLOCK, TCMP_RNE_MIN_BLOCKS
+#else
+#define TCMP_RNE_BOUNDS TCMP_RNE_BLOCK
+#endif
 template <typename T, bool DYN, bool TOOL, bool WRITE_TAU, bool WRITE_MASK, bool SCATTER = false>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(TCMP_RNE_BOUNDS)
 rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, const T *__restrict__ qdd,
                  const T *__restrict__ payload_mass, T payload_scalar, T payload_threshold,
                  T *__restrict__ tau_out, uint8_t *__restrict__ feasible_out, MaskDests dests) {
@@ -64,9 +74,9 @@ template <typename T, bool DYN, bool TOOL, bool WT, bool WM>
 static cudaError_t launch_one(int64_t n, const void *q, const void *qd, const void *qdd, const void *pm,
                               double ps, double pt, void *tau, uint8_t *mask, cudaStream_t st) {
     auto kern = rne_batch_kernel<T, DYN, TOOL, WT, WM>;
-    const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, n);
-    kern<<<grid, 128, 0, st>>>(n, (const T *)q, (const T *)qd, (const T *)qdd, (const T *)pm, (T)ps, (T)pt,
-                               (T *)tau, mask, MaskDests());
+    const int grid = grid_for(reinterpret_cast<const void *>(kern), TCMP_RNE_BLOCK, n);
+    kern<<<grid, TCMP_RNE_BLOCK, 0, st>>>(n, (const T *)q, (const T *)qd, (const T *)qdd, (const T *)pm, (T)ps, (T)pt,
+                                          (T *)tau, mask, MaskDests());
     return cudaGetLastError();
 }
 

@@ -222,6 +222,52 @@ int tcmp_ik_batch(int64_t n, const double *rot9, const double *trans3, const dou
     return TCMP_OK;
 }
 
+int tcmp_ik_select(int64_t n, const double *rot9, const double *trans3, const double *free_vals, int n_free,
+                   int free_broadcast, const double *q_ref, int ref_broadcast, const double *q_lo_host,
+                   const double *q_hi_host, int mode, double payload_scalar, double payload_threshold, int use_max_norm,
+                   double *best_q, double *best_cost, int32_t *n_valid, void *stream) {
+    if (n < 0 || n_free < 1) return fail(TCMP_ERR_INVALID_ARG, "bad n / n_free");
+    if (mode < TCMP_MODE_RNE || mode > TCMP_MODE_BASE) return fail(TCMP_ERR_INVALID_ARG, "bad mode %d", mode);
+    if (n == 0) return TCMP_OK;
+    if (!rot9 || !trans3 || !free_vals || !q_ref || !q_lo_host || !q_hi_host || !best_q || !best_cost || !n_valid)
+        return fail(TCMP_ERR_INVALID_ARG, "NULL IK-select buffer");
+    TCMP_CUDA(launch_ik_select(n, rot9, trans3, free_vals, n_free, free_broadcast, q_ref, ref_broadcast, q_lo_host,
+                               q_hi_host, mode, payload_scalar, payload_threshold, use_max_norm, best_q, best_cost,
+                               n_valid, (cudaStream_t)stream));
+    return TCMP_OK;
+}
+
+int tcmp_collision_batch(int64_t n, const double *q, int n_obs, const tcmp_obstacle *obstacles_host,
+                         const double *q_lo_host, const double *q_hi_host, double payload_radius, uint8_t *hit_out,
+                         void *stream) {
+    if (n < 0) return fail(TCMP_ERR_INVALID_ARG, "negative count");
+    if (n_obs < 0 || n_obs > TCMP_MAX_OBSTACLES) return fail(TCMP_ERR_UNSUPPORTED, "0..%d obstacles", TCMP_MAX_OBSTACLES);
+    if (n == 0) return TCMP_OK;
+    if (!q || !hit_out || !q_lo_host || !q_hi_host || (n_obs > 0 && !obstacles_host))
+        return fail(TCMP_ERR_INVALID_ARG, "NULL collision buffer");
+    TCMP_CUDA(launch_collision_batch(n, q, n_obs, obstacles_host, q_lo_host, q_hi_host, payload_radius, hit_out,
+                                     (cudaStream_t)stream));
+    return TCMP_OK;
+}
+
+int tcmp_extend_prefix(int mode, int64_t n_edges, const double *q1, const double *q2, const double *resolution_host,
+                       int n_obs, const tcmp_obstacle *obstacles_host, const double *q_lo_host, const double *q_hi_host,
+                       double payload_radius, double payload_scalar, double payload_threshold, int32_t *n_steps_out,
+                       int32_t *prefix_out, void *stream) {
+    if (int rc = check_common(mode, TCMP_F64, n_edges)) return rc;
+    if (n_obs < 0 || n_obs > TCMP_MAX_OBSTACLES) return fail(TCMP_ERR_UNSUPPORTED, "0..%d obstacles", TCMP_MAX_OBSTACLES);
+    if (n_edges == 0) return TCMP_OK;
+    if (!q1 || !q2 || !resolution_host || !q_lo_host || !q_hi_host || !n_steps_out || !prefix_out ||
+        (n_obs > 0 && !obstacles_host))
+        return fail(TCMP_ERR_INVALID_ARG, "NULL extend buffer");
+    for (int j = 0; j < 7; ++j)
+        if (!(resolution_host[j] > 0)) return fail(TCMP_ERR_INVALID_ARG, "resolution[%d] must be > 0", j);
+    TCMP_CUDA(launch_extend_prefix(mode, n_edges, q1, q2, resolution_host, n_obs, obstacles_host, q_lo_host, q_hi_host,
+                                   payload_radius, payload_scalar, payload_threshold, n_steps_out, prefix_out,
+                                   (cudaStream_t)stream));
+    return TCMP_OK;
+}
+
 int tcmp_fk_batch(int64_t n, const double *q, double *trans3, double *rot9, void *stream) {
     if (n < 0) return fail(TCMP_ERR_INVALID_ARG, "negative count");
     if (n == 0) return TCMP_OK;

@@ -48,7 +48,22 @@ cudaError_t launch_ik_batch(int64_t n, const double *rot9, const double *trans3,
                             int n_free, int free_broadcast, double *sols_out, int32_t *count_out,
                             uint8_t *status_out, cudaStream_t st);
 
+cudaError_t launch_ik_select(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
+                             int n_free, int free_broadcast, const double *q_ref, int ref_broadcast,
+                             const double *q_lo, const double *q_hi, int mode, double mass,
+                             double payload_threshold, int use_max_norm, double *best_q, double *best_cost,
+                             int32_t *n_valid, cudaStream_t st);
+
 cudaError_t launch_fk_batch(int64_t n, const double *q, double *trans3, double *rot9, cudaStream_t st);
+
+cudaError_t launch_collision_batch(int64_t n, const double *q, int n_obs, const tcmp_obstacle *obs,
+                                   const double *q_lo, const double *q_hi, double payload_radius, uint8_t *hit_out,
+                                   cudaStream_t st);
+
+cudaError_t launch_extend_prefix(int mode, int64_t n_edges, const double *q1, const double *q2,
+                                 const double *res, int n_obs, const tcmp_obstacle *obs, const double *q_lo,
+                                 const double *q_hi, double payload_radius, double mass, double payload_threshold,
+                                 int32_t *n_steps_out, int32_t *prefix_out, cudaStream_t st);
 
 cudaError_t launch_fp64_peak(int iters, double *sink, int *grid_out, int *block_out, cudaStream_t st);
 

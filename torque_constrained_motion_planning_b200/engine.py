@@ -256,6 +256,111 @@ def ik_batch(rot9, trans3, free, want_sols: bool = True, want_status: bool = Tru
     return sols, counts, status
 
 
+def ik_select(rot9, trans3, free, q_ref, payload_mass: float = 0.0, mode: str = "rne", q_lo=None, q_hi=None,
+              payload_threshold: float = PAYLOAD_THRESHOLD_TEST, norm: str = "inf"):
+    """Goal-IK selection (tcmp_ik_select): per pose, the IK solution of the free-joint sweep that is inside the
+    joint limits, passes the static torque test ``mode`` and is nearest to ``q_ref`` ([7][n] or [7]).
+    Returns (best_q [7][n], best_cost [n] (+inf = none), n_valid int32 [n]); CUDA tensors in -> CUDA tensors out,
+    NumPy in -> NumPy out."""
+    torch = _torch()
+    lib = load()
+    lim = get_limits()
+    lo = np.ascontiguousarray(lim["q_lo"] if q_lo is None else q_lo, dtype=np.float64)
+    hi = np.ascontiguousarray(lim["q_hi"] if q_hi is None else q_hi, dtype=np.float64)
+    host = not _is_cuda_tensor(rot9)
+    dev = torch.device("cuda", torch.cuda.current_device()) if host else rot9.device
+    n = int(rot9.shape[1])
+    bcast = int(len(free.shape) == 1)
+    n_free = int(free.shape[0])
+    rb = int(len(q_ref.shape) == 1)
+    with torch.cuda.device(dev):
+        r = _as_dev(rot9, "f64", (9, n), dev)
+        t = _as_dev(trans3, "f64", (3, n), dev)
+        f = _as_dev(free, "f64", (n_free,) if bcast else (n_free, n), dev)
+        ref = _as_dev(q_ref, "f64", (7,) if rb else (7, n), dev)
+        best = torch.empty((7, n), dtype=torch.float64, device=dev)
+        cost = torch.empty((n,), dtype=torch.float64, device=dev)
+        nv = torch.empty((n,), dtype=torch.int32, device=dev)
+        check(lib.tcmp_ik_select(n, _ptr(r), _ptr(t), _ptr(f), n_free, bcast, _ptr(ref), rb, _nptr(lo), _nptr(hi),
+                                 MODE[mode], float(payload_mass), float(payload_threshold),
+                                 int(norm in ("inf", "max")), _ptr(best), _ptr(cost), _ptr(nv), _stream_ptr()))
+    if host:
+        return best.cpu().numpy(), cost.cpu().numpy(), nv.cpu().numpy()
+    return best, cost, nv
+
+
+class _Obstacle(ctypes.Structure):   # tcmp_obstacle (include/tcmp.h)
+    _fields_ = [("kind", ctypes.c_int32), ("reserved", ctypes.c_int32), ("center", ctypes.c_double * 3),
+                ("half", ctypes.c_double * 3)]
+
+
+def pack_obstacles(obstacles):
+    """collision.Box / collision.Sphere objects -> ctypes array of tcmp_obstacle."""
+    arr = (_Obstacle * max(len(obstacles), 1))()
+    for i, ob in enumerate(obstacles):
+        if hasattr(ob, "radius"):
+            arr[i].kind = 1
+            arr[i].half[0] = float(ob.radius)
+        else:
+            arr[i].kind = 0
+            for r in range(3):
+                arr[i].half[r] = float(ob.half[r])
+        for r in range(3):
+            arr[i].center[r] = float(ob.center[r])
+    return arr
+
+
+def _limits_arrays(q_lo, q_hi):
+    lim = get_limits()
+    lo = np.ascontiguousarray(lim["q_lo"] if q_lo is None else q_lo, dtype=np.float64)
+    hi = np.ascontiguousarray(lim["q_hi"] if q_hi is None else q_hi, dtype=np.float64)
+    return lo, hi
+
+
+def collision_batch(q, obstacles, q_lo=None, q_hi=None, payload_radius: float = 0.0):
+    """Synthetic-scene collision predicate (tcmp_collision_batch): q ``[7][n]`` -> hit uint8 ``[n]``."""
+    torch = _torch()
+    lib = load()
+    lo, hi = _limits_arrays(q_lo, q_hi)
+    host = not _is_cuda_tensor(q)
+    dev = torch.device("cuda", torch.cuda.current_device()) if host else q.device
+    n = int(q.shape[1])
+    obs = pack_obstacles(obstacles)
+    with torch.cuda.device(dev):
+        qt = _as_dev(q, "f64", (7, n), dev)
+        hit = torch.empty((n,), dtype=torch.uint8, device=dev)
+        check(lib.tcmp_collision_batch(n, _ptr(qt), len(obstacles), ctypes.addressof(obs), _nptr(lo), _nptr(hi),
+                                       float(payload_radius), _ptr(hit), _stream_ptr()))
+    return hit.cpu().numpy() if host else hit
+
+
+def extend_prefix(q1, q2, resolution, obstacles, payload_mass: float = 0.0, mode: str = "rne", q_lo=None,
+                  q_hi=None, payload_radius: float = 0.0, payload_threshold: float = PAYLOAD_THRESHOLD_TEST):
+    """Safe-prefix length of every candidate RRT* edge q1 -> q2 (tcmp_extend_prefix): extend steps generated,
+    collision-checked and (if collision-free) statically torque-tested on the device.
+    q1/q2 ``[7][n_edges]`` -> (n_steps int32 [n_edges], prefix int32 [n_edges])."""
+    torch = _torch()
+    lib = load()
+    lo, hi = _limits_arrays(q_lo, q_hi)
+    res = np.ascontiguousarray(resolution, dtype=np.float64)
+    host = not _is_cuda_tensor(q1)
+    dev = torch.device("cuda", torch.cuda.current_device()) if host else q1.device
+    n = int(q1.shape[1])
+    obs = pack_obstacles(obstacles)
+    with torch.cuda.device(dev):
+        a = _as_dev(q1, "f64", (7, n), dev)
+        b = _as_dev(q2, "f64", (7, n), dev)
+        ns = torch.empty((n,), dtype=torch.int32, device=dev)
+        pre = torch.empty((n,), dtype=torch.int32, device=dev)
+        check(lib.tcmp_extend_prefix(MODE[mode], n, _ptr(a), _ptr(b), _nptr(res), len(obstacles),
+                                     ctypes.addressof(obs), _nptr(lo), _nptr(hi), float(payload_radius),
+                                     float(payload_mass), float(payload_threshold), _ptr(ns), _ptr(pre),
+                                     _stream_ptr()))
+    if host:
+        return ns.cpu().numpy(), pre.cpu().numpy()
+    return ns, pre
+
+
 def fk_batch(q):
     """Batched FK (tcmp_fk_batch): q ``[7][n]`` -> (trans3 ``[3][n]``, rot9 ``[9][n]``)."""
     torch = _torch()
