@@ -179,3 +179,36 @@ def test_planner_fn_force_aware_end_to_end(mode, mass):
     # determinism under fixed seeds
     traj2 = run()
     assert np.array_equal(np.array([c_.values for c_ in traj2.path]).T, q)
+
+
+def test_batched_speculative_planner_returns_valid_trajectory():
+    """speculative batched tree growth (one tcmp_extend_prefix launch per round).  Its tree differs
+    from the reference's (different use of the random stream), so the check is validity, not identity: every
+    path configuration is collision-free under the NumPy stand-in, every smoothed sample passes the oracle
+    torque test, the path starts at start_conf and ends at an IK solution of the target."""
+    from torque_constrained_motion_planning_b200 import collision, ikfast_panda_arm as ik, ik_utils
+    from torque_constrained_motion_planning_b200 import panda_primitives as pp, utils
+    scene = collision.cluttered_scene()
+    start = tuple(Q_HOME)
+    goal_q = [0.7, 0.3, 0.2, -1.9, 0.1, 2.2, 1.0]
+    pos8, rot8 = ik.get_fk(goal_q)
+    c, s = math.cos(-math.pi / 4), math.sin(-math.pi / 4)
+    Rt = np.array(rot8) @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+    pose = (tuple(np.array(pos8) + Rt @ np.array([0, 0, 0.105])), tuple(ik_utils.quat_from_matrix(Rt)))
+    random.seed(5)
+    np.random.seed(5)
+    problem = utils.Problem(robot=None, fixed=scene, payload="coke", payload_mass=3.0, execution_time=2,
+                            torque_test="rne")
+    traj = pp.planner_fn_force_aware(start, pose, problem, batch=32)
+    assert traj is not None
+    q = np.array([c_.values for c_ in traj.path])
+    qd = np.array([c_.velocities for c_ in traj.path])
+    qdd = np.array([c_.accelerations for c_ in traj.path])
+    assert np.abs(q[-1] - np.array(traj.path[-1].values)).max() == 0
+    col = collision.get_collision_fn(obstacles=scene)
+    assert not col.batch(q).any()
+    _, ok = oracle.torque_test_batch("rne", np.ascontiguousarray(q.T), np.ascontiguousarray(qd.T),
+                                     np.ascontiguousarray(qdd.T), 3.0)
+    assert ok.all()
+    t_end, _ = ik.get_fk_batch(np.ascontiguousarray(q[-1:].T))
+    assert np.abs(t_end[:, 0] - np.array(pos8)).max() < 1e-6

@@ -88,11 +88,26 @@ def link_spheres(qs):
 
 
 def get_collision_fn(body=None, joints=None, obstacles=(), attachments=(), self_collisions=False,
-                     disabled_collisions=(), custom_limits={}, payload_radius=0.0, **kwargs):
+                     disabled_collisions=(), custom_limits={}, payload_radius=0.0, backend="numpy", **kwargs):
+    """backend="numpy": the host reference of the stand-in (below).  backend="cuda": the same predicate in
+    libtcmp.so (tcmp_collision_batch); ``collision_fn.scene`` then also feeds the fused edge kernel."""
     lower, upper = Q_LOWER.copy(), Q_UPPER.copy()
     for j, (lo, hi) in custom_limits.items():
         lower[j], upper[j] = lo, hi
     obstacles = list(obstacles)
+    if backend == "cuda":
+        from . import engine
+
+        def batch_cuda(qs):
+            qs = np.atleast_2d(np.asarray(qs, dtype=float))
+            hit = engine.collision_batch(np.ascontiguousarray(qs[:, :7].T), obstacles, lower, upper, payload_radius)
+            return hit.astype(bool)
+
+        def collision_cuda(q, verbose=False):
+            return bool(batch_cuda([q])[0])
+        collision_cuda.batch = batch_cuda
+        collision_cuda.scene = {"obstacles": obstacles, "q_lo": lower, "q_hi": upper, "payload_radius": payload_radius}
+        return collision_cuda
 
     def batch(qs):
         qs = np.atleast_2d(np.asarray(qs, dtype=float))
@@ -117,4 +132,5 @@ def get_collision_fn(body=None, joints=None, obstacles=(), attachments=(), self_
         return bool(batch([q])[0])
 
     collision_fn.batch = batch
+    collision_fn.scene = {"obstacles": obstacles, "q_lo": lower, "q_hi": upper, "payload_radius": payload_radius}
     return collision_fn

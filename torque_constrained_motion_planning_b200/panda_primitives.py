@@ -30,7 +30,7 @@ from .collision import get_collision_fn
 from .ik_utils import ik_sweep, matrix_from_quat, quat_from_matrix
 from .min_jerk_v2 import coefficients_for_kernel, minjerk_coefficients, minjerk_trajectory
 from .panda_model import HAND_YAW, Q_LOWER, Q_UPPER, TAU_MAX, TOOL_Z
-from .rrt_star import rrt_star_force_aware
+from .rrt_star import rrt_star_force_aware, rrt_star_force_aware_batched
 from .utils import (MAX_DISTANCE, SELF_COLLISIONS, check_initial_end_force_aware, create_trajectory,
                     get_arm_joints, get_distance_fn, get_extend_fn, get_mass, get_max_velocities, get_sample_fn)
 
@@ -168,8 +168,9 @@ def get_dynamics_fn_v5(problem, resolutions):
 def plan_joint_motion_force_aware(body, joints, end_conf, torque_fn, dynam_fn, obstacles=[], attachments=[],
                                   self_collisions=True, disabled_collisions=set(), weights=None, radius=None,
                                   max_distance=MAX_DISTANCE, use_aabb=False, cache=True, custom_limits={},
-                                  start_conf=None, collision_fn=None, **kwargs):
-    """panda_primitives.py:327-346."""
+                                  start_conf=None, collision_fn=None, batch=0, **kwargs):
+    """panda_primitives.py:327-346.  ``batch > 0`` switches tree growth to the speculative batched variant
+    (rrt_star_force_aware_batched: ``batch`` candidate edges per kernel launch)."""
     assert len(joints) == len(end_conf)
     if (weights is None) and (radius is not None):
         weights = np.reciprocal(radius)
@@ -183,6 +184,9 @@ def plan_joint_motion_force_aware(body, joints, end_conf, torque_fn, dynam_fn, o
         raise ValueError("start_conf is required (there is no simulator to read it from)")
     if not check_initial_end_force_aware(start_conf, end_conf, collision_fn, torque_fn):
         return None, None, None, None
+    if batch > 0:
+        return rrt_star_force_aware_batched(start_conf, end_conf, weights, sample_fn, radius, collision_fn, torque_fn,
+                                            dynam_fn, max_iterations=kwargs.get("max_iterations", 50), batch=batch)
     return rrt_star_force_aware(start_conf, end_conf, distance_fn, sample_fn, extend_fn, collision_fn, torque_fn,
                                 dynam_fn, radius=[0.01], **kwargs)
 
@@ -213,9 +217,10 @@ def bi_panda_inverse_kinematics(robot, arm, gripper_link, gripper_pose, max_atte
     return None
 
 
-def planner_fn_force_aware(start_conf, pose, problem):
+def planner_fn_force_aware(start_conf, pose, problem, batch=0, collision_backend="cuda"):
     """panda_primitives.py:223-282.  Returns a Trajectory (``.path[i].values / .velocities / .accelerations /
-    .dt / .torques``) or None."""
+    .dt / .torques``) or None.  Extra keyword arguments (defaults keep the reference's behaviour):
+    ``batch`` > 0 = speculative batched tree growth; ``collision_backend`` "cuda" | "numpy"."""
     timestamp = "{}_{}".format(*str(datetime.datetime.now()).split(" "))
     robot = problem.robot
     obstacles = problem.fixed
@@ -227,7 +232,8 @@ def planner_fn_force_aware(start_conf, pose, problem):
     dynam_fn = get_dynamics_fn_v5(problem, resolutions)
     grasp = getattr(problem.payload, "grasp", None)
     gripper_pose = pose if grasp is None else grasp(pose)
-    collision_fn = get_collision_fn(robot, arm_joints, obstacles, self_collisions=SELF_COLLISIONS)
+    collision_fn = get_collision_fn(robot, arm_joints, obstacles, self_collisions=SELF_COLLISIONS,
+                                    backend=collision_backend)
     grasp_conf = None
     for _ in range(25):
         grasp_conf = bi_panda_inverse_kinematics(robot, "right", None, gripper_pose, max_attempts=25, max_time=3.5,
@@ -243,7 +249,8 @@ def planner_fn_force_aware(start_conf, pose, problem):
         return None
     out = plan_joint_motion_force_aware(robot, arm_joints, grasp_conf, torque_test, dynam_fn, obstacles=obstacles,
                                         self_collisions=SELF_COLLISIONS, max_time=50, radius=resolutions / 2,
-                                        max_iterations=50, start_conf=start_conf, collision_fn=collision_fn)
+                                        max_iterations=50, start_conf=start_conf, collision_fn=collision_fn,
+                                        batch=batch)
     approach_path, approach_vels, approach_accels, approach_dts = out
     if approach_path is None:
         print("Approach path failure")

@@ -181,3 +181,83 @@ def rrt_star_force_aware(start, goal, distance, sample, extend, collision, torqu
             if not torque_fn(path[i], velocities=vels[i], accelerations=accels[i]):
                 return None, None, None, None
     return path, vels, accels, psg
+
+
+def _refine_to(q1, q2, n_steps, k):
+    """Configuration index k (0-based) of utils.get_refine_fn(num_steps=n_steps - 1)(q1, q2)."""
+    q = np.asarray(q1, dtype=float)
+    q2 = np.asarray(q2, dtype=float)
+    out = []
+    for i in range(k + 1):
+        q = (1.0 / (n_steps - i)) * (q2 - q) + q
+        out.append(tuple(q))
+    return out
+
+
+def rrt_star_force_aware_batched(start, goal, distance_weights, sample, resolutions, collision, torque_fn, dynam_fn,
+                                 max_iterations=50, batch=64, goal_probability=.2, goal_tolerance=1e-2, rng=None):
+    """Speculative, batched tree growth: each round draws ``batch`` targets, finds each one's
+    nearest tree node on the host (vectorised) and checks ALL candidate edges -- extend steps, collision,
+    static torque test, safe prefix -- in ONE kernel launch (tcmp_extend_prefix).  Every edge with a non-empty
+    safe prefix adds a node.  Same building blocks and acceptance rules as rrt_star_force_aware (nearest by the
+    weighted distance, safe prefix, goal reached when within ``goal_tolerance``), but it consumes the random
+    stream in a different order, so its trees differ from the reference's; use strict mode for parity runs.
+    ``max_iterations`` counts rounds.  Returns (path, vels, accels, psg) or four Nones."""
+    from . import engine
+    rng = rng or np.random
+    scene = getattr(collision, "scene", None)
+    if scene is None or not hasattr(torque_fn, "mode"):
+        raise ValueError("batched growth needs collision.get_collision_fn(...) and a torque test from panda_primitives")
+    if collision(start) or collision(goal):
+        print("start config in collision")
+        return (None, None, None, None)
+    w = np.asarray(distance_weights, dtype=float)
+    res = np.asarray(resolutions, dtype=float)
+    goal_a = np.asarray(goal, dtype=float)
+    confs = [np.asarray(start, dtype=float)]
+    parent = [-1]
+    edge = [None]              # (q_from, q_target, n_steps, prefix) to regenerate the intermediate configurations
+    goal_idx = None
+    for _ in range(max_iterations):
+        targets = np.empty((batch, 7))
+        is_goal = np.zeros(batch, dtype=bool)
+        for b in range(batch):
+            if b == 0 or rng.random() < goal_probability:
+                targets[b], is_goal[b] = goal_a, True
+            else:
+                targets[b] = sample()
+        C = np.asarray(confs)
+        d2 = ((targets[:, None, :] - C[None, :, :]) ** 2 * w).sum(axis=2)
+        near = d2.argmin(axis=1)
+        q1 = C[near]
+        ns, pre = engine.extend_prefix(np.ascontiguousarray(q1.T), np.ascontiguousarray(targets.T), res,
+                                       scene["obstacles"], torque_fn.mass(), mode=torque_fn.mode,
+                                       q_lo=scene["q_lo"], q_hi=scene["q_hi"], payload_radius=scene["payload_radius"])
+        for b in range(batch):
+            if pre[b] == 0:
+                continue
+            new = np.asarray(_refine_to(q1[b], targets[b], int(ns[b]), int(pre[b]) - 1)[-1])
+            confs.append(new)
+            parent.append(int(near[b]))
+            edge.append((q1[b], targets[b], int(ns[b]), int(pre[b])))
+            if is_goal[b] and np.sqrt((w * (new - goal_a) ** 2).sum()) < goal_tolerance:
+                goal_idx = len(confs) - 1
+                break
+        if goal_idx is not None:
+            break
+    if goal_idx is None:
+        print("failed to find goal")
+        return None, None, None, None
+    chain = []
+    i = goal_idx
+    while i > 0:
+        chain.append(i)
+        i = parent[i]
+    path = [tuple(confs[0])]
+    for i in reversed(chain):
+        q_from, q_to, n_steps, prefix = edge[i]
+        path.extend(_refine_to(q_from, q_to, n_steps, prefix - 1))
+    out = dynam_fn.fused_check(path, torque_fn)
+    if not out["feasible"]:
+        return None, None, None, None
+    return out["path"], out["vels"], out["accels"], out["psg"]
