@@ -98,7 +98,8 @@ def main():
         t_cpu, out_cpu = timed(cpu_plan, 1)
         n_calls = calls["torque"]
         same = (traj is not None and out_cpu is not None and
-                np.array_equal(np.array([c_.values for c_ in traj.path]), np.array(out_cpu[0])))
+                np.array(out_cpu[0]).shape == (len(traj.path), 7) and
+                np.allclose(np.array([c_.values for c_ in traj.path]), np.array(out_cpu[0]), rtol=0, atol=1e-12))
         print(json.dumps({
             "scene": name, "samples": None if traj is None else len(traj.path),
             "gpu_strict_s": t_strict, "gpu_batched_s": t_batched,
