@@ -270,7 +270,19 @@ def main():
     if world > 1 and args.gather == "nccl":
         gather = OverlappedGather((N_STATES,), torch.uint8, dev)
     elif world > 1:
-        peer = PeerMaskBuffer(N_STATES)   # gathered [world][N_STATES] mask buffer, written by every rank's kernel
+        try:
+            peer = PeerMaskBuffer(N_STATES)   # gathered [world][N_STATES] mask buffer, written by every rank's kernel
+            ok_flag = torch.ones(1, device=dev)
+        except Exception as e:                # CUDA IPC unavailable in this container: every rank must agree
+            print("rank %d: peer-store gather unavailable (%s)" % (rank, e), file=sys.stderr)
+            ok_flag = torch.zeros(1, device=dev)
+        dist.all_reduce(ok_flag, op=dist.ReduceOp.MIN)
+        if ok_flag.item() < 1:
+            if peer is not None:
+                peer.close()
+            peer = None
+            args.gather = "nccl (p2p unavailable)"
+            gather = OverlappedGather((N_STATES,), torch.uint8, dev)
 
     def step(i, mode="rne"):
         q, qd, qdd, mass = sets[i % N_SETS]
@@ -336,6 +348,13 @@ def main():
         ms = timed(lambda i, m=mode: step(i, m), K)
         modes[mode] = world * N_STATES * K / (ms * 1e-3)
     modes["rne"] = value
+    if world == 1:   # the optional fp32 path (1e-4 relative), same launch geometry
+        f32 = [tuple(t.float() for t in s_) for s_ in sets[:2]]
+        for i in range(3):
+            engine.torque_test_batch(*f32[i % 2], mode="rne", dtype="f32")
+        ms = timed(lambda i: engine.torque_test_batch(*f32[i % 2], mode="rne", dtype="f32"), K)
+        modes["rne_f32"] = N_STATES * K / (ms * 1e-3)
+        del f32
     # mask-only rne (the planner's actual need: 177 B/state)
     ms = timed(lambda i: engine.torque_test_batch(*sets[i % N_SETS], mode="rne", want_tau=False), K)
     modes["rne_mask_only"] = world * N_STATES * K / (ms * 1e-3)
@@ -409,6 +428,7 @@ def main():
                         "peak_source": peak_src},
             },
             "modes": modes,
+            "gather": "none (N = 1)" if world == 1 else args.gather,
             "extras": extras,
             "sustained": {"value": sustained, "unit": UNIT, "steps": held,
                           "note": "same step held back to back for >= 1.5 s (device-timed); clocks sampled over it"},

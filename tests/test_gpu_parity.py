@@ -394,3 +394,23 @@ def test_extend_prefix_matches_serial_safe_path(eng):
             assert ns[e] == len(seq), (e, ns[e], len(seq))
             assert pre[e] == len(safe), (mode, e, pre[e], len(safe))
         assert (pre < ns).mean() > 0.1 and (pre == ns).mean() > 0.1
+
+
+def test_forty_million_states_int64_offsets(eng):
+    """Maximum-size property: 40 M states (each joint row 320 MB, arrays 2.2 GB, offsets beyond 2^31 bytes).
+    The input is a 1 M-state pattern tiled 40 times, so the mask must tile identically and equal the oracle's
+    mask of the pattern."""
+    import torch
+    base = 1_000_000
+    reps = 40
+    q, qd, qdd, mass = sample_states(base, seed=2)
+    _, ok_o = oracle.torque_test_batch("rne", q[:, :50_000], qd[:, :50_000], qdd[:, :50_000], mass[:50_000])
+    tile = lambda a: dev(a).repeat(*([1] * (a.ndim - 1) + [reps])).contiguous()
+    Q, V, A, M = tile(q), tile(qd), tile(qdd), tile(mass)
+    assert Q.shape == (7, base * reps)
+    _, ok = eng.torque_test_batch(Q, V, A, M, mode="rne", want_tau=False)
+    ok = ok.view(reps, base)
+    assert bool((ok == ok[0:1]).all())
+    assert np.array_equal(ok[reps - 1, :50_000].cpu().numpy(), ok_o)
+    del Q, V, A, M
+    torch.cuda.empty_cache()
