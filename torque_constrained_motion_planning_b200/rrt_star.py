@@ -24,163 +24,171 @@ INF = float("inf")
 
 
 def argmin(function, sequence):
-    values = list(sequence)
-    scores = [function(x) for x in values]
-    return values[scores.index(min(scores))]
+    """First element of ``sequence`` with the smallest ``function`` value (ties keep the earliest, as
+    ``scores.index(min(scores))`` does in the reference, rrt_star.py:9-14)."""
+    best, best_score = None, None
+    for item in sequence:
+        score = function(item)
+        if best_score is None or score < best_score:
+            best, best_score = item, score
+    return best
 
 
 class OptimalNode(object):
+    """Tree node with cost-to-come bookkeeping; same attributes and methods as the reference's node
+    (rrt_star.py:18-79): ``config``, ``parent``, ``children``, ``d`` (edge length), ``path`` (the intermediate
+    configurations of the edge), ``cost``, ``solution``, ``creation``, ``last_rewire``."""
+
+    __slots__ = ("config", "parent", "children", "d", "path", "cost", "solution", "creation", "last_rewire")
+
     def __init__(self, config, parent=None, d=0, path=[], iteration=None):
-        self.config = config
-        self.parent = parent
+        self.config, self.parent, self.d, self.path = config, parent, d, path
         self.children = set()
-        self.d = d
-        self.path = path
-        if parent is not None:
-            self.cost = parent.cost + d
-            self.parent.children.add(self)
-        else:
-            self.cost = d
         self.solution = False
-        self.creation = iteration
-        self.last_rewire = iteration
+        self.creation = self.last_rewire = iteration
+        if parent is None:
+            self.cost = d
+        else:
+            self.cost = parent.cost + d
+            parent.children.add(self)
 
     def set_solution(self, solution):
-        if self.solution is solution:
-            return
-        self.solution = solution
-        if self.parent is not None:
-            self.parent.set_solution(solution)
+        node = self
+        while node is not None and node.solution is not solution:   # stops where the flag already holds
+            node.solution = solution
+            node = node.parent
 
     def retrace(self):
-        if self.parent is None:
-            return self.path + [self.config]
-        return self.parent.retrace() + self.path + [self.config]
+        """Root-to-node list of configurations, edge interiors included."""
+        chain = []
+        node = self
+        while node is not None:
+            chain.append(node)
+            node = node.parent
+        out = []
+        for node in reversed(chain):
+            out.extend(node.path)
+            out.append(node.config)
+        return out
 
     def rewire(self, parent, d, path, iteration=None):
-        if self.solution:
+        was_solution = self.solution
+        if was_solution:
             self.parent.set_solution(False)
-        self.parent.children.remove(self)
+        self.parent.children.discard(self)
         self.parent = parent
-        self.parent.children.add(self)
-        if self.solution:
-            self.parent.set_solution(True)
-        self.d = d
-        self.path = path
+        parent.children.add(self)
+        if was_solution:
+            parent.set_solution(True)
+        self.d, self.path, self.last_rewire = d, path, iteration
         self.update()
-        self.last_rewire = iteration
 
     def update(self):
-        self.cost = self.parent.cost + self.d
-        for n in self.children:
-            n.update()
+        stack = [self]
+        while stack:                     # cost-to-come of the whole subtree, iteratively
+            node = stack.pop()
+            node.cost = node.parent.cost + node.d
+            stack.extend(node.children)
 
-    def __str__(self):
-        return self.__class__.__name__ + "(" + str(self.config) + ")"
-    __repr__ = __str__
+    def __repr__(self):
+        return "%s(%s)" % (type(self).__name__, self.config)
+    __str__ = __repr__
+
+
+def _first_failure(flags_bad):
+    flags_bad = np.asarray(flags_bad, dtype=bool)
+    return int(np.argmax(flags_bad)) if flags_bad.any() else len(flags_bad)
 
 
 def safe_path_force_aware(sequence, collision, torque):
-    """Longest prefix of ``sequence`` free of collision and within torque limits (rrt_star.py:90-98)."""
-    seq = list(sequence)
-    if not seq:
-        return []
-    col_batch = getattr(collision, "batch", None)
-    tq_batch = getattr(torque, "batch", None)
+    """Longest prefix of ``sequence`` whose configurations are collision-free AND within torque limits
+    (rrt_star.py:90-98).  Batched when both predicates offer ``.batch``; the torque test is never evaluated
+    at or beyond the first collision, exactly like the reference's short-circuit."""
+    configs = list(sequence)
+    if not configs:
+        return configs
+    col_batch, tq_batch = getattr(collision, "batch", None), getattr(torque, "batch", None)
     if col_batch is None or tq_batch is None:
-        path = []
-        for q in seq:
-            if collision(q):
+        keep = 0
+        for q in configs:
+            if collision(q) or not torque(q):
                 break
-            if not torque(q):
-                break
-            path.append(q)
-        return path
-    bad = np.asarray(col_batch(seq), dtype=bool)
-    # the reference never evaluates torque past the first collision; neither does this
-    stop = int(np.argmax(bad)) if bad.any() else len(seq)
-    if stop > 0:
-        ok = np.asarray(tq_batch(seq[:stop]), dtype=bool)
-        if not ok.all():
-            stop = int(np.argmin(ok))
-    return seq[:stop]
+            keep += 1
+        return configs[:keep]
+    keep = _first_failure(col_batch(configs))
+    if keep:
+        keep = min(keep, _first_failure(~np.asarray(tq_batch(configs[:keep]), dtype=bool)))
+    return configs[:keep]
 
 
 def rrt_star_force_aware(start, goal, distance, sample, extend, collision, torque_fn, dynam_fn, radius,
                          max_time=INF, max_iterations=INF, goal_probability=.2, informed=False,
                          strict_reference=True):
+    """rrt_star.py:151-211.  Returns ``(path, vels, accels, psg)`` or four Nones."""
+    failure = (None, None, None, None)
     if collision(start) or collision(goal):
         print("start config in collision")
-        return (None, None, None, None)
-    nodes = [OptimalNode(start)]
-    goal_n = None
-    t0 = time()
+        return failure
+    tree = [OptimalNode(start)]
+    goal_node = None
+    began = time()
+    # the reference's bound is `(t0 - time()) < max_time`, which never trips (SURVEY.md A.4)
+    within_time = (lambda: (began - time()) < max_time) if strict_reference else (lambda: (time() - began) < max_time)
     it = 0
-
-    def in_time():
-        return (t0 - time()) < max_time if strict_reference else (time() - t0) < max_time
-
-    while in_time() and it < max_iterations:
-        do_goal = goal_n is None and (it == 0 or random() < goal_probability)
-        s = goal if do_goal else sample()
-        if informed and goal_n is not None and distance(start, s) + distance(s, goal) >= goal_n.cost:
+    while within_time() and it < max_iterations:
+        aim_at_goal = goal_node is None and (it == 0 or random() < goal_probability)
+        target = goal if aim_at_goal else sample()
+        if informed and goal_node is not None and distance(start, target) + distance(target, goal) >= goal_node.cost:
             continue
         it += 1
-
-        nearest = argmin(lambda n: distance(n.config, s), nodes)
-        path = safe_path_force_aware(extend(nearest.config, s), collision, torque_fn)
-        if len(path) == 0:
+        nearest = argmin(lambda n: distance(n.config, target), tree)
+        grown = safe_path_force_aware(extend(nearest.config, target), collision, torque_fn)
+        if not grown:
             continue
-        new = OptimalNode(path[-1], parent=nearest, d=distance(nearest.config, path[-1]), path=path[:-1],
-                          iteration=it)
-        if do_goal and distance(new.config, goal) < 1e-2:
-            goal_n = new
-            goal_n.set_solution(True)
-
-        nodes.append(new)
-        # evaluated after the append, as the reference's lazy filter is (rrt_star.py:183-185)
-        neighbors = [n for n in nodes if np.all(distance(n.config, new.config) < radius)]
-        for n in neighbors:
-            d = distance(n.config, new.config)
-            if n.cost + d < new.cost:
-                path = safe_path_force_aware(extend(n.config, new.config), collision, torque_fn)
-                if len(path) != 0 and distance(new.config, path[-1]) < 1e-6:
-                    new.rewire(n, d, path[:-1], iteration=it)
-        if not strict_reference:  # the reference's second loop iterates an exhausted filter object
-            for n in neighbors:
-                if n is new:
+        tip = grown[-1]
+        fresh = OptimalNode(tip, parent=nearest, d=distance(nearest.config, tip), path=grown[:-1], iteration=it)
+        if aim_at_goal and distance(tip, goal) < 1e-2:
+            goal_node = fresh
+            goal_node.set_solution(True)
+        tree.append(fresh)
+        # the reference builds this set lazily, i.e. after the append, so `fresh` is in it (rrt_star.py:183-185)
+        near = [n for n in tree if np.all(distance(n.config, fresh.config) < radius)]
+        for n in near:                                   # better parent for the new node?
+            d = distance(n.config, fresh.config)
+            if n.cost + d < fresh.cost:
+                edge = safe_path_force_aware(extend(n.config, fresh.config), collision, torque_fn)
+                if edge and distance(fresh.config, edge[-1]) < 1e-6:
+                    fresh.rewire(n, d, edge[:-1], iteration=it)
+        if not strict_reference:                         # the reference's second loop runs on an exhausted iterator
+            for n in near:
+                if n is fresh:
                     continue
-                d = distance(new.config, n.config)
-                if new.cost + d < n.cost:
-                    path = safe_path_force_aware(extend(new.config, n.config), collision, torque_fn)
-                    if len(path) != 0 and distance(n.config, path[-1]) < 1e-6:
-                        n.rewire(new, d, path[:-1], iteration=it)
-    if goal_n is None:
+                d = distance(fresh.config, n.config)
+                if fresh.cost + d < n.cost:
+                    edge = safe_path_force_aware(extend(fresh.config, n.config), collision, torque_fn)
+                    if edge and distance(n.config, edge[-1]) < 1e-6:
+                        n.rewire(fresh, d, edge[:-1], iteration=it)
+    if goal_node is None:
         print("failed to find goal")
-        return None, None, None, None
-    rrt_path = goal_n.retrace()
-    # final check on the smoothed trajectory (rrt_star.py:203-210)
+        return failure
+    waypoints = goal_node.retrace()
+    # final check of the smoothed trajectory (rrt_star.py:203-210)
     fused = getattr(dynam_fn, "fused_check", None)
     if fused is not None:
-        # one launch: min-jerk samples + full RNE torque test of every sample
-        out = fused(rrt_path, torque_fn)
-        if not out["feasible"]:
-            return None, None, None, None
-        return out["path"], out["vels"], out["accels"], out["psg"]
-    path, psg, vels, accels = dynam_fn(rrt_path, len(rrt_path))
-    vels = vels[:len(path)]
-    accels = accels[:len(path)]
+        checked = fused(waypoints, torque_fn)            # min-jerk samples + full torque test: one launch
+        if not checked["feasible"]:
+            return failure
+        return checked["path"], checked["vels"], checked["accels"], checked["psg"]
+    path, psg, vels, accels = dynam_fn(waypoints, len(waypoints))
     if path is None:
-        return None, None, None, None
+        return failure
+    vels, accels = vels[:len(path)], accels[:len(path)]
     tq_batch = getattr(torque_fn, "batch", None)
     if tq_batch is not None:
-        if not np.asarray(tq_batch(path, velocities=vels, accelerations=accels), dtype=bool).all():
-            return None, None, None, None
+        feasible = bool(np.asarray(tq_batch(path, velocities=vels, accelerations=accels), dtype=bool).all())
     else:
-        for i in range(len(path)):
-            if not torque_fn(path[i], velocities=vels[i], accelerations=accels[i]):
-                return None, None, None, None
-    return path, vels, accels, psg
+        feasible = all(torque_fn(path[i], velocities=vels[i], accelerations=accels[i]) for i in range(len(path)))
+    return (path, vels, accels, psg) if feasible else failure
 
 
 def _refine_to(q1, q2, n_steps, k):
