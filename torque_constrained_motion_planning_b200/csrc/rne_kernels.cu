@@ -17,6 +17,17 @@ namespace tcmp {
 // the gathered buffer of EVERY rank (peer pointers mapped over NVLink/NVSwitch, CUDA IPC) at
 // dest_offset + i.  1 B/state/peer of NVLink traffic rides under an FP64-bound kernel; no extra launch,
 // no host-side collective call (which costs more CPU time than this 63 us kernel runs).
+#ifndef TCMP_PREFETCH
+#define TCMP_PREFETCH 0   // 0 = off (default: measured 9 % SLOWER on, ptxas goes from 126 to 202 registers), 1 = prefetch.global.L1, 2 = .L2
+#endif
+__device__ __forceinline__ void prefetch_line(const void *p) {
+#if TCMP_PREFETCH == 2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+
 struct MaskDests {
     uint8_t *p[TCMP_MAX_PEERS];
     int n;
@@ -41,6 +52,25 @@ rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, c
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         T qs[7], vs[7], as[7], tau[7];
+#if TCMP_PREFETCH
+        // ncu (round 1): 0.92 long-scoreboard stalls per issued instruction -- each state starts by waiting
+        // ~800 cycles for its 22 DRAM loads with only ~3 warps per scheduler to cover them.  Prefetching the
+        // NEXT state's rows while this one computes costs no registers and turns those loads into cache hits.
+        {
+            const int64_t nx = i + stride;
+            if (nx < n) {
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    prefetch_line(q + j * n + nx);
+                    if constexpr (DYN) {
+                        prefetch_line(qd + j * n + nx);
+                        prefetch_line(qdd + j * n + nx);
+                    }
+                }
+                if (payload_mass) prefetch_line(payload_mass + nx);
+            }
+        }
+#endif
 #pragma unroll
         for (int j = 0; j < 7; ++j) qs[j] = __ldcs(q + j * n + i);
         if constexpr (DYN) {
