@@ -378,7 +378,7 @@ def main():
     hq, hqd, hqdd, hm = (pin(a) for a in host0)
     htau = torch.empty((7, N_STATES), dtype=torch.float64).pin_memory()
     hok = torch.empty((N_STATES,), dtype=torch.uint8).pin_memory()
-    ws = engine.Workspace(chunk_states=1 << 17)
+    ws = engine.Workspace(chunk_states=1 << 18)
     nq, nqd, nqdd, nm, ntau, nok = (t.numpy() for t in (hq, hqd, hqdd, hm, htau, hok))
 
     def e2e_step(_i):

@@ -1,0 +1,78 @@
+"""GPU: BASELINE.json configs at FULL size, compared element by element with the CPU checkers (the C oracle
+runs 1 M states in well under a second on the box's host cores; the compiled reference IKFast runs 25 M solves
+in a few seconds)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import Q_HI, Q_LO, sample_edges, sample_states
+
+pytestmark = pytest.mark.gpu
+NT = len(os.sched_getaffinity(0))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from torque_constrained_motion_planning_b200 import engine
+    return engine
+
+
+def dev(x):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(x), device="cuda")
+
+
+@pytest.mark.parametrize("mode", ["rne", "nov", "dyn"])
+def test_config2_one_million_states(eng, mode):
+    """configs[1]: 1M synthetic states, fp64, seed 2 -- torques <= 1e-9 N.m and masks bit-exact on
+    ALL 1M states, plus the margin statement (no state within 1e-9 of a limit)."""
+    q, qd, qdd, mass = sample_states(1_000_000, seed=2)
+    tau_o, ok_o = oracle.torque_test_batch(mode, q, qd, qdd, mass, nthreads=NT)
+    tau, ok = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode=mode)
+    err = np.abs(tau.cpu().numpy() - tau_o).max()
+    assert err < 1e-9, err
+    assert np.array_equal(ok.cpu().numpy(), ok_o)
+    lim = np.array([87.0, 87, 87, 87, 12, 12])[:, None]
+    assert np.abs(lim - np.abs(tau_o[:6])).min() > 1e-9
+    # host-buffer path on the same 1M states
+    tau_h, ok_h = eng.torque_test_batch(q, qd, qdd, mass, mode=mode)
+    assert np.array_equal(ok_h, ok_o) and np.abs(tau_h - tau_o).max() < 1e-9
+
+
+def test_config3_one_million_poses_times_25(eng):
+    """configs[2]: 1M reachable poses x 25 free values (own j7 first, then uniform) -- solution COUNT bit-exact on all
+    25M solves against the compiled, unmodified reference; values checked on a slice."""
+    import torch
+    rng = np.random.default_rng(3)
+    n, nf = 1_000_000, 25
+    q = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, n))
+    trans, rot = eng.fk_batch(dev(q))
+    free = np.empty((nf, n))
+    free[0] = q[6]
+    free[1:] = rng.uniform(-2.8973, 2.8973, size=(nf - 1, n))
+    _, counts, status = eng.ik_batch(rot, trans, dev(free), want_sols=False)
+    rot_h, trans_h = rot.cpu().numpy(), trans.cpu().numpy()
+    _, counts_ref = oracle.ref_ik_batch(rot_h, trans_h, free, want_sols=False, nthreads=NT)
+    c = counts.cpu().numpy()
+    mism = np.nonzero(c != counts_ref)[0]
+    assert len(mism) == 0, (len(mism), mism[:10], c[mism[:10]], counts_ref[mism[:10]])
+    assert (c.reshape(n, nf)[:, 0] >= 1).all()
+    assert int(status.max()) == 0
+    m = 20_000
+    sols, _, _ = eng.ik_batch(rot[:, :m].contiguous(), trans[:, :m].contiguous(), dev(free[:, :m]))
+    sols_ref, cr = oracle.ref_ik_batch(rot_h[:, :m], trans_h[:, :m], free[:, :m], nthreads=NT)
+    s = sols.cpu().numpy()
+    d = np.abs((s - sols_ref + np.pi) % (2 * np.pi) - np.pi)          # same order, compare modulo 2 pi
+    valid = np.arange(8)[None, :, None] < cr[:, None, None]
+    assert (d * valid).max() < 1e-9
+
+
+def test_config4_hundred_thousand_edges(eng):
+    """configs[3]: 100k edges x 64 min-jerk waypoints, rne, 5 kg -- first-failure index bit-exact on every edge."""
+    qa, qb = sample_edges(100_000, seed=4)
+    ff_o = oracle.edge_feasibility("rne", qa, qb, 64, 5.0, nthreads=NT)
+    ff = eng.edge_feasibility(dev(qa), dev(qb), 64, 5.0, mode="rne")
+    assert np.array_equal(ff.cpu().numpy(), ff_o)
+    assert 0.6 < (ff_o == 64).mean() < 0.9
