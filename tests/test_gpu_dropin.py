@@ -212,3 +212,29 @@ def test_batched_speculative_planner_returns_valid_trajectory():
     assert ok.all()
     t_end, _ = ik.get_fk_batch(np.ascontiguousarray(q[-1:].T))
     assert np.abs(t_end[:, 0] - np.array(pos8)).max() < 1e-6
+
+
+def test_ikfast_and_franka_front_ends():
+    """ikfast.py:136-188 / franka_ik_fast.py:36-62 call shapes on the CUDA solver."""
+    from torque_constrained_motion_planning_b200 import franka_ik_fast as fr, ikfast as ikf, ikfast_panda_arm as ik
+    from torque_constrained_motion_planning_b200 import ik_utils
+    assert ikf.is_ik_compiled(fr.PANDA_INFO)
+    goal_q = [0.7, 0.3, 0.2, -1.9, 0.1, 2.2, 1.0]
+    pose8 = ik_utils.compute_forward_kinematics(ik.get_fk, goal_q)
+    gen = ikf.ikfast_inverse_kinematics(None, fr.PANDA_INFO, None, pose8, max_attempts=25, current_conf=goal_q,
+                                        rng=random.Random(1))
+    confs = list(gen)
+    assert len(confs) >= 1 and min(np.abs(np.array(c) - np.array(goal_q)).max() for c in confs) < 1e-9
+    closest = list(ikf.closest_inverse_kinematics(None, fr.PANDA_INFO, None, pose8, max_attempts=25, verbose=False,
+                                                  current_conf=goal_q, rng=random.Random(1)))
+    d = [np.abs(np.array(c) - np.array(goal_q)).max() for c in closest]
+    assert d == sorted(d) and d[0] < 1e-9
+    # tool-frame front end: pose of panda_grasptarget
+    c, s = math.cos(-math.pi / 4), math.sin(-math.pi / 4)
+    R8 = ik_utils.matrix_from_quat(pose8[1])
+    Rt = R8 @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+    tool_pose = (tuple(np.array(pose8[0]) + Rt @ np.array([0, 0, 0.105])), tuple(ik_utils.quat_from_matrix(Rt)))
+    conf = fr.sample_tool_ik(None, "right", tool_pose, current_conf=goal_q)
+    assert conf is not None and not ik_utils.violates_limits(conf)
+    t, _ = ik.get_fk_batch(np.array(conf).reshape(7, 1))
+    assert np.abs(t[:, 0] - np.array(pose8[0])).max() < 1e-6
