@@ -21,34 +21,58 @@
 namespace tcmp {
 namespace ik {
 
-__global__ void __launch_bounds__(128)
+// Thread mapping is solve-major (s = pose * n_free + f, the ABI's output order): the 32 solves of a warp own one
+// contiguous 32 x 448 B span of sols_out.  Each lane emits its solutions into a padded shared-memory row
+// (57 doubles: an odd stride keeps 64-bit accesses conflict-free), then the warp copies the span out with fully
+// coalesced 256 B stores -- instead of 56 scattered 8 B stores per lane that each dirty their own 32 B sector.
+constexpr int kSolRow = 57;
+
+constexpr int kIkBlock = 64;   // 2 warps x 32 rows x 57 doubles = 29 KB of static shared memory (< 48 KB)
+
+template <bool WRITE_SOLS>
+__global__ void __launch_bounds__(kIkBlock)
 ik_kernel(int64_t n, int n_free, int free_broadcast, const double *__restrict__ rot9,
           const double *__restrict__ trans3, const double *__restrict__ free_vals, double *__restrict__ sols_out,
           int32_t *__restrict__ count_out, uint8_t *__restrict__ status_out) {
+    __shared__ double stage[WRITE_SOLS ? (kIkBlock / 32) * 32 * kSolRow : 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t total = n * n_free;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += stride) {
-        // f-major mapping inside the kernel: consecutive threads take consecutive poses, so the SoA
-        // pose loads coalesce; the OUTPUT index stays pose*n_free + f as the ABI states.
-        const int f = (int)(s / n);
-        const int64_t p = s - (int64_t)f * n;
-        double R[9];
+    const int64_t rounds = (total + stride - 1) / stride;
+    for (int64_t r = 0; r < rounds; ++r) {
+        const int64_t s = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool live = s < total;
+        double *row = WRITE_SOLS ? &stage[(wib * 32 + lane) * kSolRow] : nullptr;
+        if (live) {
+            const int64_t p = s / n_free;
+            const int f = (int)(s - p * n_free);
+            double R[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) R[i] = __ldg(rot9 + i * n + p);
-        const double j6 = free_broadcast ? __ldg(free_vals + f) : __ldg(free_vals + (int64_t)f * n + p);
-        Pose P;
-        prepare_pose(R, __ldg(trans3 + p), __ldg(trans3 + n + p), __ldg(trans3 + 2 * n + p), j6, P);
-
-        const int64_t o = p * n_free + f;
-        Emit out;
-        out.sols = sols_out ? sols_out + o * 56 : nullptr;
-        out.count = 0;
-        out.status = 0;
-        solve_one(P, out);
-        if (out.sols)
-            for (int k = (out.count < 8 ? out.count : 8) * 7; k < 56; ++k) out.sols[k] = 0.0;
-        count_out[o] = out.count;
-        if (status_out) status_out[o] = (uint8_t)out.status;
+            for (int i = 0; i < 9; ++i) R[i] = __ldg(rot9 + i * n + p);
+            const double j6 = free_broadcast ? __ldg(free_vals + f) : __ldg(free_vals + (int64_t)f * n + p);
+            Pose P;
+            prepare_pose(R, __ldg(trans3 + p), __ldg(trans3 + n + p), __ldg(trans3 + 2 * n + p), j6, P);
+            Emit out;
+            out.sols = row;
+            out.count = 0;
+            out.status = 0;
+            solve_one(P, out);
+            if (WRITE_SOLS)
+                for (int k = (out.count < 8 ? out.count : 8) * 7; k < 56; ++k) row[k] = 0.0;
+            count_out[s] = out.count;
+            if (status_out) status_out[s] = (uint8_t)out.status;
+        }
+        if (WRITE_SOLS) {
+            __syncwarp();
+            const int64_t warp_first = s - lane;                         // first solve of this warp's span
+            const int64_t span = (total - warp_first) < 32 ? (total - warp_first) : 32;
+            if (span > 0) {
+                double *dst = sols_out + warp_first * 56;
+                const double *src = &stage[wib * 32 * kSolRow];
+                for (int idx = lane; idx < (int)span * 56; idx += 32) dst[idx] = src[(idx / 56) * kSolRow + idx % 56];
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -94,9 +118,15 @@ fk_kernel(int64_t n, const double *__restrict__ q, double *__restrict__ trans3, 
 cudaError_t launch_ik_batch(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
                             int n_free, int free_broadcast, double *sols_out, int32_t *count_out,
                             uint8_t *status_out, cudaStream_t st) {
-    const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel), 128, n * n_free);
-    ik::ik_kernel<<<grid, 128, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out, count_out,
-                                        status_out);
+    if (sols_out) {
+        const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel<true>), ik::kIkBlock, n * n_free);
+        ik::ik_kernel<true><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out,
+                                                  count_out, status_out);
+    } else {
+        const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel<false>), ik::kIkBlock, n * n_free);
+        ik::ik_kernel<false><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out,
+                                                   count_out, status_out);
+    }
     return cudaGetLastError();
 }
 
