@@ -1,0 +1,79 @@
+"""GPU: own bounds checks (compute-sanitizer is closed on this pool): every output buffer is carved out of a
+larger sentinel-filled allocation; after the call the guard bands on both sides must be untouched, at ragged
+sizes that end mid-warp / mid-CTA."""
+import numpy as np
+import pytest
+
+from conftest import Q_HI, Q_LO, sample_edges, sample_states
+
+pytestmark = pytest.mark.gpu
+
+GUARD = 4096
+
+
+def guarded(torch, shape, dtype):
+    n = int(np.prod(shape))
+    sentinel = {torch.float64: -7.25e300, torch.float32: -7.25e30, torch.uint8: 0xA5, torch.int32: -1234567}[dtype]
+    big = torch.full((n + 2 * GUARD,), sentinel, dtype=dtype, device="cuda")
+    return big, big[GUARD:GUARD + n].view(*shape), sentinel
+
+
+def intact(big, n, sentinel):
+    return bool((big[:GUARD] == sentinel).all()) and bool((big[GUARD + n:] == sentinel).all())
+
+
+@pytest.mark.parametrize("n", [1, 31, 129, 1000, 75777])
+def test_output_guard_bands(n):
+    import torch
+    from torque_constrained_motion_planning_b200 import _lib
+    lib = _lib.load()
+    st = int(torch.cuda.current_stream().cuda_stream)
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+    q, qd, qdd, m = (dev(a) for a in sample_states(n, seed=n))
+    # tcmp_rne_batch
+    bt, tau, s_t = guarded(torch, (7, n), torch.float64)
+    bm, mask, s_m = guarded(torch, (n,), torch.uint8)
+    for mode in range(4):
+        _lib.check(lib.tcmp_rne_batch(mode, 0, n, q.data_ptr(), qd.data_ptr(), qdd.data_ptr(), m.data_ptr(), 0.0, 0.01,
+                                      tau.data_ptr(), mask.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert intact(bt, 7 * n, s_t) and intact(bm, n, s_m)
+    assert bool((mask <= 1).all()) and bool(torch.isfinite(tau).all())
+    # tcmp_edge_feasibility
+    qa, qb = (dev(a) for a in sample_edges(n, seed=n))
+    bf, ff, s_f = guarded(torch, (n,), torch.int32)
+    for W in (1, 33, 64):
+        _lib.check(lib.tcmp_edge_feasibility(0, 0, n, W, qa.data_ptr(), qb.data_ptr(), 5.0, 0.01, 0, ff.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert intact(bf, n, s_f) and bool(((ff >= 0) & (ff <= W)).all())
+    # tcmp_fk_batch / tcmp_ik_batch
+    b1, trans, s1 = guarded(torch, (3, n), torch.float64)
+    b2, rot, s2 = guarded(torch, (9, n), torch.float64)
+    _lib.check(lib.tcmp_fk_batch(n, q.data_ptr(), trans.data_ptr(), rot.data_ptr(), st))
+    nf = 3
+    free = dev(np.random.default_rng(n).uniform(Q_LO[6], Q_HI[6], size=(nf, n)))
+    b3, sols, s3 = guarded(torch, (n * nf, 8, 7), torch.float64)
+    b4, cnt, s4 = guarded(torch, (n * nf,), torch.int32)
+    b5, stat, s5 = guarded(torch, (n * nf,), torch.uint8)
+    _lib.check(lib.tcmp_ik_batch(n, rot.data_ptr(), trans.data_ptr(), free.data_ptr(), nf, 0, sols.data_ptr(),
+                                 cnt.data_ptr(), stat.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert intact(b1, 3 * n, s1) and intact(b2, 9 * n, s2)
+    assert intact(b3, n * nf * 56, s3) and intact(b4, n * nf, s4) and intact(b5, n * nf, s5)
+    assert bool(((cnt >= 0) & (cnt <= 8)).all())
+    assert bool((sols != s3).all())                      # every slot written (solutions or zero fill)
+    # tcmp_traj_feasibility
+    from torque_constrained_motion_planning_b200 import min_jerk_v2
+    pts = np.random.default_rng(n).uniform(Q_LO, Q_HI, size=(4, 7))
+    coeffs = dev(min_jerk_v2.coefficients_for_kernel(min_jerk_v2.minjerk_coefficients(pts)))
+    S = max(1, n // 3)
+    ns = 3 * S
+    outs = [guarded(torch, (7, ns), torch.float64) for _ in range(4)]
+    bk, msk, sk = guarded(torch, (ns,), torch.uint8)
+    first = torch.full((1,), ns, dtype=torch.int32, device="cuda")
+    _lib.check(lib.tcmp_traj_feasibility(0, 0, 3, S, coeffs.data_ptr(), 5.0, 0.01, outs[0][1].data_ptr(),
+                                         outs[1][1].data_ptr(), outs[2][1].data_ptr(), outs[3][1].data_ptr(),
+                                         msk.data_ptr(), first.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert all(intact(b, 7 * ns, s) for b, _, s in outs) and intact(bk, ns, sk)
+    assert 0 <= int(first.item()) <= ns
