@@ -60,10 +60,23 @@ def main():
     ms = timed(lambda: D.sharded_edge_feasibility(a, b, W, 5.0, mode="rne"))
     ff, _ = D.sharded_edge_feasibility(a, b, W, 5.0, mode="rne")
     assert torch.equal(ff, engine.edge_feasibility(a, b, W, 5.0, mode="rne")), "sharded != single-GPU first_fail"
+    single = engine.edge_feasibility(a, b, W, 5.0, mode="rne")
+    # fused form: every rank's edge kernel stores its block's indices into all ranks' gathered buffers (NVLink peers)
+    lo, hi = D.shard_bounds(E, rank, world)
+    per = max(D.shard_bounds(E, r, world)[1] - D.shard_bounds(E, r, world)[0] for r in range(world))
+    buf = D.PeerIndexBuffer(per)
+    a_blk, b_blk = a[:, lo:hi].contiguous(), b[:, lo:hi].contiguous()
+    ms_p2p = timed(lambda: buf.edge_feasibility(a_blk, b_blk, W, 5.0, mode="rne"))
+    buf.edge_feasibility(a_blk, b_blk, W, 5.0, mode="rne")
+    buf.barrier()
+    got = torch.cat([buf.gathered[r, : D.shard_bounds(E, r, world)[1] - D.shard_bounds(E, r, world)[0]] for r in range(world)])
+    assert torch.equal(got, single), "peer-store gather != single-GPU first_fail"
     if rank == 0:
-        print(json.dumps({"workload": "configs[3]: 100k edges x 64 waypoints, rne, 5 kg", "n_gpus": world,
-                          "edges_per_s": E / (ms * 1e-3), "ms": ms, "gather": "NCCL all_gather_into_tensor (int32 first_fail)",
+        print(json.dumps({"workload": "configs[3]: 100k edges x 64 waypoints, rne, 5 kg (strong scaling)", "n_gpus": world,
+                          "edges_per_s_fused_p2p": E / (ms_p2p * 1e-3), "ms_fused_p2p": ms_p2p,
+                          "edges_per_s_nccl": E / (ms * 1e-3), "ms_nccl": ms,
                           "feasible_fraction": float((ff == W).float().mean().item())}))
+    buf.close()
 
     # ---- IK: poses sharded, counts + solution sets all-gathered --------------------------------------------------
     n, nf = 200_000, 25
@@ -78,10 +91,25 @@ def main():
     sols, counts, _ = D.sharded_ik(rot, trans, fd)
     s1, c1, _ = engine.ik_batch(rot, trans, fd)
     assert torch.equal(counts, c1) and torch.equal(sols, s1), "sharded != single-GPU IK"
+    # what a planner needs from goal IK is ONE configuration per pose: fused select, gather 56 B per pose
+    ref = torch.as_tensor(q, device=dev)
+    lo, hi = D.shard_bounds(n, rank, world)
+
+    def select_step():
+        best, cost, nv = engine.ik_select(rot[:, lo:hi].contiguous(), trans[:, lo:hi].contiguous(),
+                                          fd[:, lo:hi].contiguous(), ref[:, lo:hi].contiguous(), 3.0, mode="rne")
+        return D.all_gather_ragged(best.T.contiguous(), n)
+
+    ms_sel = timed(select_step, reps=5)
+    best_all = select_step()
+    b1, _, _ = engine.ik_select(rot, trans, fd, ref, 3.0, mode="rne")
+    assert torch.equal(best_all, b1.T.contiguous()), "sharded != single-GPU IK select"
     if rank == 0:
-        print(json.dumps({"workload": "configs[2] slice: 200k poses x 25 free values, counts + [8][7] sets gathered",
-                          "n_gpus": world, "solves_per_s": n * nf / (ms * 1e-3), "ms": ms,
-                          "gather": "NCCL all_gather_into_tensor (2.2 GB of solution sets + counts)"}))
+        print(json.dumps({"workload": "configs[2] slice: 200k poses x 25 free values (strong scaling)", "n_gpus": world,
+                          "solves_per_s_sets_gathered": n * nf / (ms * 1e-3), "ms_sets_gathered": ms,
+                          "solves_per_s_select_gathered": n * nf / (ms_sel * 1e-3), "ms_select_gathered": ms_sel,
+                          "note": "sets: NCCL all-gather of 2.2 GB of [8][7] solution sets; select: fused limits + "
+                                  "static torque test + nearest, 56 B per pose gathered"}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -107,6 +107,13 @@ int tcmp_edge_feasibility(int mode, int dtype, int64_t n_edges, int n_waypoints,
                           const void *qb, double payload_scalar, double payload_threshold,
                           int static_only, int32_t *first_fail_out, void *stream);
 
+/* Multi-GPU form of tcmp_edge_feasibility (fp64): the first-failure index of edge e is stored into
+ * dest_first_fail[d][dest_offset + e] (int32) for every d < n_dest -- the gathered buffers of all ranks, peers
+ * mapped with tcmp_peer_open.  See tcmp_rne_batch_scatter. */
+int tcmp_edge_feasibility_scatter(int mode, int64_t n_edges, int n_waypoints, const void *qa, const void *qb,
+                                  double payload_scalar, double payload_threshold, int static_only, int n_dest,
+                                  void *const *dest_first_fail, int64_t dest_offset, void *stream);
+
 /*
  * Final-trajectory check (rrt_star.py:203-210 + panda_primitives.py:299-316): evaluate the
  * piecewise quintic with coefficients coeffs[seg][joint][6] (a0..a5, unit segment duration,

@@ -36,6 +36,8 @@ SIGNATURES = {
     "tcmp_peer_open": (_i32, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "tcmp_peer_close": (_i32, [_vp]),
     "tcmp_edge_feasibility": (_i32, [_i32, _i32, _i64, _i32, _vp, _vp, _f64, _f64, _i32, _vp, _vp]),
+    "tcmp_edge_feasibility_scatter": (_i32, [_i32, _i64, _i32, _vp, _vp, _f64, _f64, _i32, _i32, ctypes.POINTER(_vp),
+                                             _i64, _vp]),
     "tcmp_traj_feasibility": (_i32, [_i32, _i32, _i32, _i32, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tcmp_ik_batch": (_i32, [_i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "tcmp_ik_select": (_i32, [_i64, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _f64, _f64, _i32, _vp, _vp,

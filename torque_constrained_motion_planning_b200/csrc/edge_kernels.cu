@@ -21,10 +21,19 @@ template <typename T> __device__ __forceinline__ T linspace_sample(int i, int n,
     return (T)t;
 }
 
+// Multi-GPU form: lane 0 stores the edge's first-failure index into the gathered buffer of every rank (peer
+// pointers over NVLink, see tcmp_rne_batch_scatter) instead of a local array + a separate NCCL all-gather.
+struct IndexDests {
+    int32_t *p[TCMP_MAX_PEERS];
+    int n;          // 0 = plain local output through `first_fail`
+    int64_t offset;
+};
+
 template <typename T, bool DYN, bool TOOL>
 __global__ void __launch_bounds__(128)
 edge_kernel(int64_t n_edges, int W, double interval, double step, const T *__restrict__ qa,
-            const T *__restrict__ qb, T mass, T payload_threshold, int32_t *__restrict__ first_fail) {
+            const T *__restrict__ qb, T mass, T payload_threshold, int32_t *__restrict__ first_fail,
+            IndexDests dests) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -64,7 +73,15 @@ edge_kernel(int64_t n_edges, int W, double interval, double step, const T *__res
                 break;
             }
         }
-        if (lane == 0) first_fail[e] = first;
+        if (lane == 0) {
+            if (dests.n == 0) {
+                first_fail[e] = first;
+            } else {
+#pragma unroll
+                for (int d = 0; d < TCMP_MAX_PEERS; ++d)
+                    if (d < dests.n) dests.p[d][dests.offset + e] = first;
+            }
+        }
     }
 }
 
@@ -110,33 +127,53 @@ static void linspace_params(int n, double *interval, double *step) {
 
 template <typename T, bool DYN, bool TOOL>
 static cudaError_t launch_edge_t(int64_t n_edges, int W, const void *qa, const void *qb, double ps, double pt,
-                                 int32_t *ff, cudaStream_t st) {
+                                 int32_t *ff, const IndexDests &dests, cudaStream_t st) {
     double interval, step;
     linspace_params(W, &interval, &step);
     auto kern = edge_kernel<T, DYN, TOOL>;
     const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, n_edges * 32);
-    kern<<<grid, 128, 0, st>>>(n_edges, W, interval, step, (const T *)qa, (const T *)qb, (T)ps, (T)pt, ff);
+    kern<<<grid, 128, 0, st>>>(n_edges, W, interval, step, (const T *)qa, (const T *)qb, (T)ps, (T)pt, ff, dests);
     return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t launch_edge_typed(int mode, int64_t n_edges, int W, const void *qa, const void *qb,
-                                     double ps, double pt, int static_only, int32_t *ff, cudaStream_t st) {
+                                     double ps, double pt, int static_only, int32_t *ff, const IndexDests &dests,
+                                     cudaStream_t st) {
     const bool dynamic = (mode != TCMP_MODE_NOV) && !static_only;
     const bool tool = (mode == TCMP_MODE_DYN);
     if (dynamic) {
-        if (tool) return launch_edge_t<T, true, true>(n_edges, W, qa, qb, ps, pt, ff, st);
-        return launch_edge_t<T, true, false>(n_edges, W, qa, qb, ps, pt, ff, st);
+        if (tool) return launch_edge_t<T, true, true>(n_edges, W, qa, qb, ps, pt, ff, dests, st);
+        return launch_edge_t<T, true, false>(n_edges, W, qa, qb, ps, pt, ff, dests, st);
     }
-    if (tool) return launch_edge_t<T, false, true>(n_edges, W, qa, qb, ps, pt, ff, st);
-    return launch_edge_t<T, false, false>(n_edges, W, qa, qb, ps, pt, ff, st);
+    if (tool) return launch_edge_t<T, false, true>(n_edges, W, qa, qb, ps, pt, ff, dests, st);
+    return launch_edge_t<T, false, false>(n_edges, W, qa, qb, ps, pt, ff, dests, st);
 }
 
 cudaError_t launch_edge_feasibility(int mode, int dtype, int64_t n_edges, int W, const void *qa, const void *qb,
                                     double ps, double pt, int static_only, int32_t *ff, cudaStream_t st) {
+    IndexDests none;
+    none.n = 0;
+    none.offset = 0;
+    for (int i = 0; i < TCMP_MAX_PEERS; ++i) none.p[i] = nullptr;
     if (mode == TCMP_MODE_BASE) return launch_fill<int32_t>(n_edges, ff, W, st);
-    if (dtype == TCMP_F64) return launch_edge_typed<double>(mode, n_edges, W, qa, qb, ps, pt, static_only, ff, st);
-    return launch_edge_typed<float>(mode, n_edges, W, qa, qb, ps, pt, static_only, ff, st);
+    if (dtype == TCMP_F64) return launch_edge_typed<double>(mode, n_edges, W, qa, qb, ps, pt, static_only, ff, none, st);
+    return launch_edge_typed<float>(mode, n_edges, W, qa, qb, ps, pt, static_only, ff, none, st);
+}
+
+cudaError_t launch_edge_feasibility_scatter(int mode, int64_t n_edges, int W, const void *qa, const void *qb,
+                                            double ps, double pt, int static_only, int n_dest,
+                                            void *const *dest_ff, int64_t dest_offset, cudaStream_t st) {
+    IndexDests d;
+    d.n = n_dest;
+    d.offset = dest_offset;
+    for (int i = 0; i < TCMP_MAX_PEERS; ++i) d.p[i] = i < n_dest ? (int32_t *)dest_ff[i] : nullptr;
+    if (mode == TCMP_MODE_BASE) {
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < n_dest && e == cudaSuccess; ++i) e = launch_fill<int32_t>(n_edges, d.p[i] + dest_offset, W, st);
+        return e;
+    }
+    return launch_edge_typed<double>(mode, n_edges, W, qa, qb, ps, pt, static_only, nullptr, d, st);
 }
 
 template <typename T, bool DYN, bool TOOL>

@@ -199,6 +199,22 @@ int tcmp_edge_feasibility(int mode, int dtype, int64_t n_edges, int n_waypoints,
     return TCMP_OK;
 }
 
+int tcmp_edge_feasibility_scatter(int mode, int64_t n_edges, int n_waypoints, const void *qa, const void *qb,
+                                  double payload_scalar, double payload_threshold, int static_only, int n_dest,
+                                  void *const *dest_first_fail, int64_t dest_offset, void *stream) {
+    if (int rc = check_common(mode, TCMP_F64, n_edges)) return rc;
+    if (n_waypoints < 1) return fail(TCMP_ERR_INVALID_ARG, "n_waypoints must be >= 1");
+    if (n_dest < 1 || n_dest > TCMP_MAX_PEERS || !dest_first_fail || dest_offset < 0)
+        return fail(TCMP_ERR_INVALID_ARG, "bad destination list");
+    for (int i = 0; i < n_dest; ++i)
+        if (!dest_first_fail[i]) return fail(TCMP_ERR_INVALID_ARG, "dest_first_fail[%d] is NULL", i);
+    if (n_edges == 0) return TCMP_OK;
+    if (!qa || !qb) return fail(TCMP_ERR_INVALID_ARG, "NULL edge buffer");
+    TCMP_CUDA(launch_edge_feasibility_scatter(mode, n_edges, n_waypoints, qa, qb, payload_scalar, payload_threshold,
+                                              static_only, n_dest, dest_first_fail, dest_offset, (cudaStream_t)stream));
+    return TCMP_OK;
+}
+
 int tcmp_traj_feasibility(int mode, int dtype, int n_seg, int samples_per_segment, const double *coeffs,
                           double payload_scalar, double payload_threshold, void *q_out, void *qd_out, void *qdd_out,
                           void *tau_out, uint8_t *feasible_out, int32_t *first_fail_out, void *stream) {

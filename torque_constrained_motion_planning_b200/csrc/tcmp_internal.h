@@ -39,6 +39,10 @@ cudaError_t launch_edge_feasibility(int mode, int dtype, int64_t n_edges, int n_
                                     const void *qb, double payload_scalar, double payload_threshold,
                                     int static_only, int32_t *first_fail_out, cudaStream_t st);
 
+cudaError_t launch_edge_feasibility_scatter(int mode, int64_t n_edges, int n_waypoints, const void *qa, const void *qb,
+                                            double payload_scalar, double payload_threshold, int static_only,
+                                            int n_dest, void *const *dest_ff, int64_t dest_offset, cudaStream_t st);
+
 cudaError_t launch_traj_feasibility(int mode, int dtype, int n_seg, int samples_per_segment,
                                     const double *coeffs, double payload_scalar, double payload_threshold,
                                     void *q_out, void *qd_out, void *qdd_out, void *tau_out,

@@ -151,8 +151,8 @@ class OverlappedGather:
 class _DevArray:
     """Minimal __cuda_array_interface__ holder so torch can view memory owned by libtcmp.so."""
 
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr, n, typestr="|u1"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 class PeerMaskBuffer:
@@ -161,6 +161,9 @@ class PeerMaskBuffer:
     peer-store epilogue over NVLink/NVSwitch.  Each rank allocates its copy with tcmp_peer_alloc (cudaMalloc +
     CUDA IPC), the 64-byte handles are exchanged once through torch.distributed, and peers are mapped with
     tcmp_peer_open.  After ``torque_test`` + a stream sync + ``barrier()`` every rank holds every mask."""
+
+    itemsize = 1
+    typestr = "|u1"
 
     def __init__(self, n_per_rank: int, group=None):
         import ctypes
@@ -174,7 +177,7 @@ class PeerMaskBuffer:
         if self.world > 8:
             raise ValueError("at most 8 peers (one NVSwitch node)")
         self.n = int(n_per_rank)
-        nbytes = self.n * self.world
+        nbytes = self.n * self.world * self.itemsize
         self._own = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
         self._check(self._lib.tcmp_peer_alloc(ctypes.byref(self._own), nbytes, handle))
@@ -195,7 +198,8 @@ class PeerMaskBuffer:
                 self._peers.append(p)
                 ptrs[r] = p.value
         self._ptrs = ptrs
-        self.gathered = torch.as_tensor(_DevArray(self._own.value, nbytes), device=dev).view(self.world, self.n)
+        self.gathered = torch.as_tensor(_DevArray(self._own.value, self.n * self.world, self.typestr),
+                                        device=dev).view(self.world, self.n)
 
     def torque_test(self, q, qd=None, qdd=None, payload_mass=0.0, mode="rne", payload_threshold=0.01,
                     want_tau=True):
@@ -228,3 +232,25 @@ class PeerMaskBuffer:
             self.gathered = None
             self._lib.tcmp_peer_free(self._own)
             self._own = None
+
+
+class PeerIndexBuffer(PeerMaskBuffer):
+    """Gathered ``int32 [world][n_per_rank]`` buffer for per-edge first-failure indices, written by every rank's
+    edge kernel directly (tcmp_edge_feasibility_scatter) -- configs[3] "sharded at 2/4/8 B200" without a
+    collective call on the step."""
+
+    itemsize = 4
+    typestr = "<i4"
+
+    def edge_feasibility(self, qa, qb, n_waypoints=64, payload_mass=0.0, mode="rne", payload_threshold=0.01,
+                         static_only=False):
+        """Evaluate this rank's block of edges (qa/qb [7][n] CUDA fp64 tensors); row ``rank`` of ``gathered`` on
+        every rank receives the first-failure indices."""
+        import torch
+        from ._lib import MODE
+        n = int(qa.shape[1])
+        assert n <= self.n
+        self._check(self._lib.tcmp_edge_feasibility_scatter(
+            MODE[mode], n, int(n_waypoints), int(qa.data_ptr()), int(qb.data_ptr()), float(payload_mass),
+            float(payload_threshold), int(static_only), self.world, self._ptrs, self.rank * self.n,
+            int(torch.cuda.current_stream().cuda_stream)))
