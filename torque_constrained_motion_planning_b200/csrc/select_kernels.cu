@@ -4,7 +4,7 @@
 // value, drops solutions outside the joint limits (ikfast.py:167, franka_ik_fast.py:55-57), keeps the
 // one nearest to the current configuration (closest_inverse_kinematics, ikfast.py:172-188, max-norm by
 // default; select_solution, ik_utils.py:43-52) and then requires the static torque test of that grasp
-// configuration (panda_primitives.py:263).  Here one thread owns one pose: it loops over the sweep,
+// configuration (panda_primitives.py:263).  Here one warp owns one pose and its lanes the values of the sweep: each lane
 // solves, filters by limits, runs the STATIC torque test (rne_core<double, false, TOOL>) on every
 // surviving solution and keeps the nearest feasible one -- no solution set ever leaves the SM.
 #include "ik_core.cuh"
@@ -17,6 +17,10 @@ struct JointLimits {
     double lo[7], hi[7];
 };
 
+// One warp per pose; lanes own the free-joint values of the sweep (32 per round).  Each lane solves, filters
+// and torque-tests its <= 8 solutions and keeps its nearest survivor; a shuffle arg-min over (cost, free index)
+// picks the pose's winner -- ties resolve to the earliest free value, then solver order, exactly as a serial scan
+// in sweep order would.
 template <bool TOOL>
 __global__ void __launch_bounds__(128)
 ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__restrict__ rot9,
@@ -24,10 +28,12 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
                  const double *__restrict__ q_ref, int ref_broadcast, JointLimits lim, int check_torque,
                  double mass, double payload_threshold, int use_max_norm, double *__restrict__ best_q,
                  double *__restrict__ best_cost, int32_t *__restrict__ n_valid) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double mp_inertial = TOOL ? 0.0 : (mass > payload_threshold ? mass : 0.0);
     const double mp_tool = TOOL ? mass : 0.0;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    for (int64_t p = warp; p < n; p += n_warps) {
         double R[9], ref[7];
 #pragma unroll
         for (int i = 0; i < 9; ++i) R[i] = __ldg(rot9 + i * n + p);
@@ -36,8 +42,9 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
         const double tx = __ldg(trans3 + p), ty = __ldg(trans3 + n + p), tz = __ldg(trans3 + 2 * n + p);
         double bq[7] = {0, 0, 0, 0, 0, 0, 0};
         double bcost = INFINITY;
+        int bf = 0x7fffffff;   // free index of the lane's best (tie-break key)
         int valid = 0;
-        for (int f = 0; f < n_free; ++f) {
+        for (int f = lane; f < n_free; f += 32) {
             const double j6 = free_broadcast ? __ldg(free_vals + f) : __ldg(free_vals + (int64_t)f * n + p);
             ik::Pose P;
             ik::prepare_pose(R, tx, ty, tz, j6, P);
@@ -61,8 +68,6 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
                     cmax = fmax(cmax, d);
                 }
                 if (!inside) continue;
-                const double cost = use_max_norm ? cmax : sqrt(c2);
-                if (!(cost < bcost) && !check_torque) { ++valid; continue; }
                 if (check_torque) {
                     double tau[7];
                     const double z[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -70,17 +75,32 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
                     if (!within_limits<double>(tau)) continue;
                 }
                 ++valid;
-                if (cost < bcost) {
+                const double cost = use_max_norm ? cmax : sqrt(c2);
+                if (cost < bcost) {   // strict: the earliest (f, s) wins ties within the lane
                     bcost = cost;
+                    bf = f;
 #pragma unroll
                     for (int j = 0; j < 7; ++j) bq[j] = q[j];
                 }
             }
         }
+        // warp arg-min over (cost, free index) and sum of survivors
+        double wc = bcost;
+        int wf = bf, wl = lane;
 #pragma unroll
-        for (int j = 0; j < 7; ++j) best_q[j * n + p] = bq[j];
-        best_cost[p] = bcost;
-        n_valid[p] = valid;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double oc = __shfl_xor_sync(0xffffffffu, wc, off);
+            const int of = __shfl_xor_sync(0xffffffffu, wf, off);
+            const int ol = __shfl_xor_sync(0xffffffffu, wl, off);
+            valid += __shfl_xor_sync(0xffffffffu, valid, off);
+            if (oc < wc || (oc == wc && of < wf)) { wc = oc; wf = of; wl = ol; }
+        }
+        if (lane == wl) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) best_q[j * n + p] = bq[j];
+            best_cost[p] = bcost;
+            n_valid[p] = valid;
+        }
     }
 }
 
@@ -96,12 +116,12 @@ cudaError_t launch_ik_select(int64_t n, const double *rot9, const double *trans3
     }
     const int check = mode != TCMP_MODE_BASE;
     if (mode == TCMP_MODE_DYN) {
-        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<true>), 128, n);
+        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<true>), 128, n * 32);
         ik_select_kernel<true><<<grid, 128, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref,
                                                      ref_broadcast, lim, check, mass, payload_threshold, use_max_norm,
                                                      best_q, best_cost, n_valid);
     } else {
-        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<false>), 128, n);
+        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<false>), 128, n * 32);
         ik_select_kernel<false><<<grid, 128, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref,
                                                       ref_broadcast, lim, check, mass, payload_threshold, use_max_norm,
                                                       best_q, best_cost, n_valid);
