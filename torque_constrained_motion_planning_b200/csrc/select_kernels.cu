@@ -17,22 +17,33 @@ struct JointLimits {
     double lo[7], hi[7];
 };
 
-// One warp per pose; lanes own the free-joint values of the sweep (32 per round).  Each lane solves, filters
-// and torque-tests its <= 8 solutions and keeps its nearest survivor; a shuffle arg-min over (cost, free index)
-// picks the pose's winner -- ties resolve to the earliest free value, then solver order, exactly as a serial scan
-// in sweep order would.
+// One warp per pose, two dense phases (the first version ran the torque test inside the per-lane solution loop:
+// with 0 / 4 / 8 solutions per lane and ~1 in 4 inside the joint limits the warp executed 8 sparse RNE rounds
+// per sweep and the kernel took 6x longer than the IK alone).
+//   A. lanes own the free-joint values of the sweep (32 per round): solve, filter by joint limits, and append
+//      every survivor (q, cost, key = f*8 + s) to a per-warp shared-memory candidate list with a ballot/popc
+//      prefix -- the list is in sweep order.
+//   B. lanes own CANDIDATES: one static torque test each (dense), then a shuffle arg-min over (cost, key) picks
+//      the nearest feasible configuration; ties go to the earliest key, as a serial scan in sweep order would.
+constexpr int kSelWarps = 2;            // warps per CTA
+constexpr int kSelCap = 256;            // 32 lanes x 8 solutions: a round can never overflow the list
+constexpr int kSelRow = 9;              // q[7], cost, key (as double) -- odd stride, conflict-free 64-bit rows
+
 template <bool TOOL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kSelWarps * 32)
 ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__restrict__ rot9,
                  const double *__restrict__ trans3, const double *__restrict__ free_vals,
                  const double *__restrict__ q_ref, int ref_broadcast, JointLimits lim, int check_torque,
                  double mass, double payload_threshold, int use_max_norm, double *__restrict__ best_q,
                  double *__restrict__ best_cost, int32_t *__restrict__ n_valid) {
-    const int lane = threadIdx.x & 31;
+    __shared__ double cand_all[kSelWarps][kSelCap * kSelRow];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *cand = cand_all[wib];
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double mp_inertial = TOOL ? 0.0 : (mass > payload_threshold ? mass : 0.0);
     const double mp_tool = TOOL ? mass : 0.0;
+    const unsigned lt_mask = (1u << lane) - 1u;
     for (int64_t p = warp; p < n; p += n_warps) {
         double R[9], ref[7];
 #pragma unroll
@@ -40,65 +51,93 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
 #pragma unroll
         for (int j = 0; j < 7; ++j) ref[j] = ref_broadcast ? __ldg(q_ref + j) : __ldg(q_ref + j * n + p);
         const double tx = __ldg(trans3 + p), ty = __ldg(trans3 + n + p), tz = __ldg(trans3 + 2 * n + p);
+        double wc = INFINITY;     // this lane's best feasible candidate so far: cost, key, configuration
+        int wk = 0x7fffffff, valid = 0;
         double bq[7] = {0, 0, 0, 0, 0, 0, 0};
-        double bcost = INFINITY;
-        int bf = 0x7fffffff;   // free index of the lane's best (tie-break key)
-        int valid = 0;
-        for (int f = lane; f < n_free; f += 32) {
-            const double j6 = free_broadcast ? __ldg(free_vals + f) : __ldg(free_vals + (int64_t)f * n + p);
-            ik::Pose P;
-            ik::prepare_pose(R, tx, ty, tz, j6, P);
+        for (int fbase = 0; fbase < n_free; fbase += 32) {
+            // ---- phase A: IK + joint-limit filter for up to 32 free values ----
+            const int f = fbase + lane;
             double sols[56];
-            ik::Emit out;
-            out.sols = sols;
-            out.count = 0;
-            out.status = 0;
-            ik::solve_one(P, out);
-            const int cnt = out.count < 8 ? out.count : 8;
-            for (int s = 0; s < cnt; ++s) {
-                double q[7];
-                bool inside = true;
-                double c2 = 0.0, cmax = 0.0;
+            int cnt = 0;
+            if (f < n_free) {
+                const double j6 = free_broadcast ? __ldg(free_vals + f) : __ldg(free_vals + (int64_t)f * n + p);
+                ik::Pose P;
+                ik::prepare_pose(R, tx, ty, tz, j6, P);
+                ik::Emit out;
+                out.sols = sols;
+                out.count = 0;
+                out.status = 0;
+                ik::solve_one(P, out);
+                cnt = out.count < 8 ? out.count : 8;
+            }
+            int ncand = 0;
+            for (int sidx = 0; sidx < 8; ++sidx) {       // warp-synchronous: every lane walks all 8 slots
+                bool keep = sidx < cnt;
+                double q[7], c2 = 0.0, cmax = 0.0;
+                if (keep) {
 #pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    q[j] = sols[s * 7 + j];
-                    inside = inside && !(q[j] < lim.lo[j]) && !(q[j] > lim.hi[j]);   // violates_limits
-                    const double d = fabs(q[j] - ref[j]);
-                    c2 += d * d;
-                    cmax = fmax(cmax, d);
+                    for (int j = 0; j < 7; ++j) {
+                        q[j] = sols[sidx * 7 + j];
+                        keep = keep && !(q[j] < lim.lo[j]) && !(q[j] > lim.hi[j]);   // violates_limits
+                        const double d = fabs(q[j] - ref[j]);
+                        c2 += d * d;
+                        cmax = fmax(cmax, d);
+                    }
                 }
-                if (!inside) continue;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    // the list order is irrelevant: the KEY (f*8 + s) carries the sweep order for tie-breaks
+                    double *row = cand + (ncand + __popc(m & lt_mask)) * kSelRow;
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) row[j] = q[j];
+                    row[7] = use_max_norm ? cmax : sqrt(c2);
+                    row[8] = (double)(f * 8 + sidx);
+                }
+                ncand += __popc(m);
+            }
+            __syncwarp();
+            // ---- phase B: one candidate per lane, dense static torque tests ----
+            for (int c = lane; c < ncand; c += 32) {
+                const double *row = cand + c * kSelRow;
+                double q[7];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) q[j] = row[j];
+                bool ok = true;
                 if (check_torque) {
                     double tau[7];
                     const double z[7] = {0, 0, 0, 0, 0, 0, 0};
                     rne_core<double, false, TOOL>(q, z, z, mp_inertial, mp_tool, tau);
-                    if (!within_limits<double>(tau)) continue;
+                    ok = within_limits<double>(tau);
                 }
-                ++valid;
-                const double cost = use_max_norm ? cmax : sqrt(c2);
-                if (cost < bcost) {   // strict: the earliest (f, s) wins ties within the lane
-                    bcost = cost;
-                    bf = f;
+                if (ok) {
+                    ++valid;
+                    const double cost = row[7];
+                    const int key = (int)row[8];
+                    if (cost < wc || (cost == wc && key < wk)) {
+                        wc = cost;
+                        wk = key;
 #pragma unroll
-                    for (int j = 0; j < 7; ++j) bq[j] = q[j];
+                        for (int j = 0; j < 7; ++j) bq[j] = q[j];
+                    }
                 }
             }
+            __syncwarp();   // the list is rewritten by the next sweep round
         }
-        // warp arg-min over (cost, free index) and sum of survivors
-        double wc = bcost;
-        int wf = bf, wl = lane;
+        // warp arg-min over (cost, key), sum of survivors
+        double bc = wc;
+        int bk = wk, bl = lane;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
-            const double oc = __shfl_xor_sync(0xffffffffu, wc, off);
-            const int of = __shfl_xor_sync(0xffffffffu, wf, off);
-            const int ol = __shfl_xor_sync(0xffffffffu, wl, off);
+            const double oc = __shfl_xor_sync(0xffffffffu, bc, off);
+            const int ok2 = __shfl_xor_sync(0xffffffffu, bk, off);
+            const int ol = __shfl_xor_sync(0xffffffffu, bl, off);
             valid += __shfl_xor_sync(0xffffffffu, valid, off);
-            if (oc < wc || (oc == wc && of < wf)) { wc = oc; wf = of; wl = ol; }
+            if (oc < bc || (oc == bc && ok2 < bk) || (oc == bc && ok2 == bk && ol < bl)) { bc = oc; bk = ok2; bl = ol; }
         }
-        if (lane == wl) {
+        if (lane == bl) {       // with no survivor every lane ties at (inf, INT_MAX): lane 0 writes zeros
 #pragma unroll
             for (int j = 0; j < 7; ++j) best_q[j * n + p] = bq[j];
-            best_cost[p] = bcost;
+            best_cost[p] = bc;
             n_valid[p] = valid;
         }
     }
@@ -116,13 +155,13 @@ cudaError_t launch_ik_select(int64_t n, const double *rot9, const double *trans3
     }
     const int check = mode != TCMP_MODE_BASE;
     if (mode == TCMP_MODE_DYN) {
-        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<true>), 128, n * 32);
-        ik_select_kernel<true><<<grid, 128, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref,
+        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<true>), kSelWarps * 32, n * 32);
+        ik_select_kernel<true><<<grid, kSelWarps * 32, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref,
                                                      ref_broadcast, lim, check, mass, payload_threshold, use_max_norm,
                                                      best_q, best_cost, n_valid);
     } else {
-        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<false>), 128, n * 32);
-        ik_select_kernel<false><<<grid, 128, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref,
+        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<false>), kSelWarps * 32, n * 32);
+        ik_select_kernel<false><<<grid, kSelWarps * 32, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref,
                                                       ref_broadcast, lim, check, mass, payload_threshold, use_max_norm,
                                                       best_q, best_cost, n_valid);
     }
