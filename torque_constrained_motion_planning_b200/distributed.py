@@ -202,7 +202,7 @@ class PeerMaskBuffer:
                                         device=dev).view(self.world, self.n)
 
     def torque_test(self, q, qd=None, qdd=None, payload_mass=0.0, mode="rne", payload_threshold=0.01,
-                    want_tau=True):
+                    want_tau=True, out_tau=None):
         """Evaluate this rank's block (q/qd/qdd [7][n] CUDA tensors) and store its mask into row ``rank`` of the
         gathered buffer on EVERY rank.  Returns tau [7][n] (or None)."""
         import torch
@@ -210,7 +210,8 @@ class PeerMaskBuffer:
         n = int(q.shape[1])
         assert n <= self.n
         scalar, pm = (float(payload_mass), None) if np.ndim(payload_mass) == 0 else (0.0, payload_mass)
-        tau = torch.empty((7, n), dtype=torch.float64, device=q.device) if want_tau else None
+        tau = (out_tau if out_tau is not None else torch.empty((7, n), dtype=torch.float64, device=q.device)) \
+            if want_tau else None
         ptr = lambda t: None if t is None else int(t.data_ptr())
         self._check(self._lib.tcmp_rne_batch_scatter(
             MODE[mode], DTYPE["f64"], n, ptr(q), ptr(qd), ptr(qdd), ptr(pm), scalar, float(payload_threshold),

@@ -54,6 +54,9 @@ def _as_dev(x, dtype, shape, device):
     torch = _torch()
     if x is None:
         return None
+    if torch.is_tensor(x) and x.dtype == _tdtype(dtype) and x.device == device and x.is_contiguous() \
+            and tuple(x.shape) == tuple(shape):
+        return x          # hot path: already a usable buffer, no dispatcher round trips
     if not torch.is_tensor(x):
         x = torch.as_tensor(np.asarray(x), device=device)
     x = x.to(device=device, dtype=_tdtype(dtype)).contiguous()
@@ -115,9 +118,10 @@ def device_count() -> int:
 
 def torque_test_batch(q, qd=None, qdd=None, payload_mass=0.0, mode: str = "rne", dtype: str = "f64",
                       payload_threshold: float = PAYLOAD_THRESHOLD_TEST, want_tau: bool = True,
-                      want_mask: bool = True, workspace: Optional[Workspace] = None):
+                      want_mask: bool = True, workspace: Optional[Workspace] = None, out_tau=None, out_mask=None):
     """Batched torque test (tcmp_rne_batch).  q/qd/qdd ``[7][n]``; payload_mass scalar or ``[n]``.
-    Returns ``(tau [7][n] or None, feasible uint8 [n] or None)``."""
+    Returns ``(tau [7][n] or None, feasible uint8 [n] or None)``.  Device path only: ``out_tau`` / ``out_mask``
+    are optional preallocated CUDA tensors to write into (no allocation on the call)."""
     lib = load()
     if not (want_tau or want_mask):
         raise ValueError("nothing to compute")
@@ -136,8 +140,10 @@ def torque_test_batch(q, qd=None, qdd=None, payload_mass=0.0, mode: str = "rne",
             qdt = _as_dev(qd, dtype, (7, n), dev)
             qddt = _as_dev(qdd, dtype, (7, n), dev)
             pmt = _as_dev(pm, dtype, (n,), dev)
-            tau = torch.empty((7, n), dtype=_tdtype(dtype), device=dev) if want_tau else None
-            mask = torch.empty((n,), dtype=torch.uint8, device=dev) if want_mask else None
+            tau = (out_tau if out_tau is not None else torch.empty((7, n), dtype=_tdtype(dtype), device=dev)) \
+                if want_tau else None
+            mask = (out_mask if out_mask is not None else torch.empty((n,), dtype=torch.uint8, device=dev)) \
+                if want_mask else None
             check(lib.tcmp_rne_batch(MODE[mode], DTYPE[dtype], n, _ptr(qt), _ptr(qdt), _ptr(qddt), _ptr(pmt), scalar,
                                      float(payload_threshold), _ptr(tau), _ptr(mask), _stream_ptr()))
         return tau, mask
