@@ -31,6 +31,12 @@ __device__ __forceinline__ void prefetch_line(const void *p) {
 #ifndef TCMP_PDL
 #define TCMP_PDL 1
 #endif
+#ifndef TCMP_DOUBLE_BUFFER
+#define TCMP_DOUBLE_BUFFER 1   // measured +3..5 % with 3 resident CTAs (168 registers, no spills)
+#endif
+#if TCMP_DOUBLE_BUFFER && !defined(TCMP_RNE_MIN_BLOCKS)
+#define TCMP_RNE_MIN_BLOCKS 3
+#endif
 
 struct MaskDests {
     uint8_t *p[TCMP_MAX_PEERS];
@@ -38,7 +44,8 @@ struct MaskDests {
     int64_t offset;
 };
 
-// Launch bounds: 128-thread CTAs; ptxas settles on 126 registers (4 CTAs / SM) with no spills.  Capping
+// Launch bounds: 128-thread CTAs.  Single-buffered, ptxas settles on 128 registers (4 CTAs / SM, no spills); the
+// double-buffered default asks for 3 CTAs / SM (168 registers, no spills).  Capping
 // lower (TCMP_RNE_MIN_BLOCKS=5) trades spills for occupancy -- measured slower, see profiles/.
 #ifndef TCMP_RNE_BLOCK
 #define TCMP_RNE_BLOCK 128
@@ -61,6 +68,58 @@ rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, c
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
+#if TCMP_DOUBLE_BUFFER
+    // Register double buffering: the NEXT grid-stride state's 22 inputs are loaded before the current state's
+    // recursion starts, so a warp never sits in a long-scoreboard stall with nothing to issue.
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T qs[7], vs[7], as[7], mass;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        qs[j] = __ldcs(q + j * n + i);
+        if constexpr (DYN) { vs[j] = __ldcs(qd + j * n + i); as[j] = __ldcs(qdd + j * n + i); }
+    }
+    mass = payload_mass ? __ldcs(payload_mass + i) : payload_scalar;
+    for (;;) {
+        const int64_t nx = i + stride;
+        const bool more = nx < n;
+        T nq[7], nv[7], na[7], nm = payload_scalar;
+        if (more) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                nq[j] = __ldcs(q + j * n + nx);
+                if constexpr (DYN) { nv[j] = __ldcs(qd + j * n + nx); na[j] = __ldcs(qdd + j * n + nx); }
+            }
+            if (payload_mass) nm = __ldcs(payload_mass + nx);
+        }
+        T tau[7];
+        const T mp_inertial = TOOL ? T(0) : (mass > payload_threshold ? mass : T(0));
+        const T mp_tool = TOOL ? mass : T(0);
+        rne_core<T, DYN, TOOL>(qs, vs, as, mp_inertial, mp_tool, tau);
+        if constexpr (WRITE_TAU) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) __stcs(tau_out + j * n + i, tau[j]);
+        }
+        if constexpr (SCATTER) {
+            const uint8_t m = (uint8_t)within_limits<T>(tau);
+#pragma unroll
+            for (int d = 0; d < TCMP_MAX_PEERS; ++d)
+                if (d < dests.n) dests.p[d][dests.offset + i] = m;
+        } else if constexpr (WRITE_MASK) {
+            __stcs(feasible_out + i, (uint8_t)within_limits<T>(tau));
+        }
+        if (!more) break;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            qs[j] = nq[j];
+            if constexpr (DYN) { vs[j] = nv[j]; as[j] = na[j]; }
+        }
+        mass = nm;
+        i = nx;
+    }
+}
+#else
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         T qs[7], vs[7], as[7], tau[7];
@@ -111,6 +170,7 @@ rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, c
         }
     }
 }
+#endif
 
 template <typename T, bool DYN, bool TOOL, bool WT, bool WM>
 static cudaError_t launch_one(int64_t n, const void *q, const void *qd, const void *qdd, const void *pm,
