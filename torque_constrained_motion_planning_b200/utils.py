@@ -159,6 +159,10 @@ class Trajectory:
         self.bodies = bodies
         self.ts = ts
 
+    def save_npz(self, path):
+        """Write the trajectory dump of collect_data.py:109-131 (np.savez with keys q, qd, qdd, torques, ts)."""
+        np.savez(path, **self.to_npz_dict())
+
     def to_npz_dict(self):
         """The on-disk schema of collect_data.py:109-131: q, qd, qdd, torques, ts."""
         return {
