@@ -136,8 +136,10 @@ int tcmp_traj_feasibility(int mode, int dtype, int n_seg, int samples_per_segmen
  *   free_vals [n_free][n], or [n_free] when free_broadcast != 0;
  *   solve index s = pose*n_free + f;  sols_out [n*n_free][8][7] (may be NULL: counts only),
  *   count_out [n*n_free] = number of solutions (0..8).
- *   status_out [n*n_free] or NULL: bit 0 set when a solve entered a degenerate branch of the
- *   reference's decision tree that this library resolves with its own closed form.
+ *   status_out [n*n_free] or NULL: bit 0 = the solve entered a singular branch of the reference's decision tree
+ *   (resolved like the reference: shoulder singularity, j2 pinned to 0); bit 1 = a special case of the generated
+ *   solver that is not implemented (never observed on 100 M random + special-value solves); bit 2 = non-finite
+ *   input (the reference throws from IKFAST_ASSERT; here the solve returns 0 solutions).
  */
 int tcmp_ik_batch(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
                   int n_free, int free_broadcast, double *sols_out, int32_t *count_out,

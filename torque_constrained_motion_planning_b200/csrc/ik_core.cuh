@@ -100,7 +100,8 @@ struct Emit {
 
 enum : unsigned {
     kStatusDegenerate = 1u,  // a singular branch of the decision tree was entered (and resolved if bit 1 is clear)
-    kStatusUnresolved = 2u   // ... one of the generated solver's special cases this restatement does not implement
+    kStatusUnresolved = 2u,  // ... one of the generated solver's special cases this restatement does not implement
+    kStatusInvalid = 4u      // non-finite target: the reference trips IKFAST_ASSERT (:57,:138) and throws; here 0 solutions
 };
 
 TCMP_HD inline void emit_solution(Emit &out, double j0, double j1, double j2, double j3, double j4,
@@ -250,6 +251,10 @@ TCMP_HD inline void solve_one(const Pose &P, Emit &out) {
     // j3 from |p|^2 (:461-485)
     const double arg3 = 0.986881610513004 + (-3.89793688895078) * P.pp + 0.686036892455338 * cn +
                         (-0.686036892455338) * sn;
+    if (!(arg3 == arg3)) {   // NaN anywhere in the pose / free value ends up here
+        out.status |= kStatusInvalid;
+        return;
+    }
     if (!in_unit(arg3)) return;
     const double a3 = clamp_asin(arg3);
     Root j3r[2] = {make_root(1.10379390314189 + a3), make_root(4.24538655673168 - a3)};
