@@ -23,8 +23,13 @@
 #include <stdint.h>
 #ifdef __CUDACC__
 #define TCMP_HD __host__ __device__
+// Measured: making make_root / atan2_checked / solve_shoulder real (noinline) functions and not unrolling the root
+// loops halves the SASS (140 KB -> 72 KB) but is 15 % SLOWER (call ABI + 432 B of local stack), so everything
+// stays inlined; define TCMP_OUTLINE as __noinline__ to reproduce.
+#define TCMP_OUTLINE
 #else
 #define TCMP_HD
+#define TCMP_OUTLINE
 #endif
 
 namespace tcmp {
@@ -65,7 +70,7 @@ TCMP_HD inline double wrap_pi(double a) {  // the "> IKPI -= IK2PI / < -IKPI += 
     return a;
 }
 // IKatan2WithCheck (:219-231): valid iff neither is NaN and |y| >= 1e-7 or |x| > 1e-7.
-TCMP_HD inline bool atan2_checked(double y, double x, double *out) {
+TCMP_HD TCMP_OUTLINE inline bool atan2_checked(double y, double x, double *out) {
     if (isnan(y) || isnan(x)) return false;
     if (!(fabs(y) >= kAtan2Thresh || fabs(x) > kAtan2Thresh)) return false;
     *out = atan2(y, x);
@@ -75,7 +80,7 @@ TCMP_HD inline bool atan2_checked(double y, double x, double *out) {
 struct Root {
     double a, s, c;  // wrapped angle; sin/cos of the unwrapped angle, as the solver computes them
 };
-TCMP_HD inline Root make_root(double angle) {
+TCMP_HD TCMP_OUTLINE inline Root make_root(double angle) {
     Root r;
     sincos(angle, &r.s, &r.c);
     r.a = wrap_pi(angle);
@@ -115,7 +120,7 @@ TCMP_HD inline void emit_solution(Emit &out, double j0, double j1, double j2, do
 
 // Residual ZYZ problem (rotationfunction0, :3115): with j3,j4,j5,j6 fixed, M = R_{3..6}^T R must
 // equal Rz(j0) Ry(j1) Rz(j2).
-TCMP_HD inline void solve_shoulder(const Pose &P, const Root &j3, const Root &j4, const Root &j5, Emit &out) {
+TCMP_HD TCMP_OUTLINE inline void solve_shoulder(const Pose &P, const Root &j3, const Root &j4, const Root &j5, Emit &out) {
     // M = (Rz(j3') ...)^T R, written as three successive frame changes of the columns of R
     // (:3122-3147): first about the tool axis by j6, then j5, j4, j3.
     double M[3][3];
@@ -242,6 +247,15 @@ TCMP_HD inline void prepare_pose(const double R[9], double tx, double ty, double
     P.npx = P.px * P.r[0][0] + P.py * P.r[1][0] + P.pz * P.r[2][0];
     P.npy = P.px * P.r[0][1] + P.py * P.r[1][1] + P.pz * P.r[2][1];
     P.npz = P.px * P.r[0][2] + P.py * P.r[1][2] + P.pz * P.r[2][2];
+}
+
+// The solver's first gate (:461-462): the asin argument of j3.  0 = no solution for this (pose, free value),
+// 1 = continue with solve_one, 2 = non-finite input.  ~45 % of the solves of a free-joint sweep stop here.
+TCMP_HD inline int screen_pose(const Pose &P) {
+    const double arg3 = 0.986881610513004 + (-3.89793688895078) * P.pp + 0.686036892455338 * (P.c6 * P.npx) +
+                        (-0.686036892455338) * (P.npy * P.s6);
+    if (!(arg3 == arg3)) return 2;
+    return in_unit(arg3) ? 1 : 0;
 }
 
 // One solve (IKSolver::ComputeIk, :412).

@@ -76,6 +76,112 @@ ik_kernel(int64_t n, int n_free, int free_broadcast, const double *__restrict__ 
     }
 }
 
+// Compacting form (ncu on the kernel above: 14 of 32 lanes active, because ~45 % of a sweep's solves fail the
+// solver's first gate and return at once while their warp-mates run all 8 branches).  Each warp walks chunks of 32
+// consecutive solves; lanes SCREEN their solve (pose reduction + the j3 gate), finish the rejected ones on the spot
+// and push the survivors' indices into a per-warp shared-memory queue (ballot / popc prefix).  Whenever 32
+// survivors are queued, the warp solves them with every lane busy.  Solution sets are staged in shared memory and
+// written row by row with coalesced stores.
+constexpr int kQueueCap = 64;   // <= 31 left over + 32 pushed per chunk
+
+__device__ __forceinline__ void load_pose(int64_t s, int64_t n, int n_free, int free_broadcast,
+                                          const double *__restrict__ rot9, const double *__restrict__ trans3,
+                                          const double *__restrict__ free_vals, Pose &P) {
+    const int64_t p = s / n_free;
+    const int f = (int)(s - p * n_free);
+    double R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = __ldg(rot9 + i * n + p);
+    const double j6 = free_broadcast ? __ldg(free_vals + f) : __ldg(free_vals + (int64_t)f * n + p);
+    prepare_pose(R, __ldg(trans3 + p), __ldg(trans3 + n + p), __ldg(trans3 + 2 * n + p), j6, P);
+}
+
+template <bool WRITE_SOLS>
+__global__ void __launch_bounds__(kIkBlock)
+ik_kernel_compact(int64_t n, int n_free, int free_broadcast, const double *__restrict__ rot9,
+                  const double *__restrict__ trans3, const double *__restrict__ free_vals,
+                  double *__restrict__ sols_out, int32_t *__restrict__ count_out, uint8_t *__restrict__ status_out) {
+    __shared__ double stage[WRITE_SOLS ? (kIkBlock / 32) * 32 * kSolRow : 1];
+    __shared__ long long queue_all[kIkBlock / 32][kQueueCap];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    long long *queue = queue_all[wib];
+    double *rows = &stage[WRITE_SOLS ? wib * 32 * kSolRow : 0];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t total = n * n_free;
+    const int64_t n_chunks = (total + 31) / 32;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int qn = 0;   // warp-uniform queue length
+
+    auto solve_batch = [&](int cnt) {   // the first `cnt` queue entries, one per lane
+        long long s = -1;
+        if (lane < cnt) {
+            s = queue[lane];
+            Pose P;
+            load_pose(s, n, n_free, free_broadcast, rot9, trans3, free_vals, P);
+            Emit out;
+            out.sols = WRITE_SOLS ? rows + lane * kSolRow : nullptr;
+            out.count = 0;
+            out.status = 0;
+            solve_one(P, out);
+            if (WRITE_SOLS)
+                for (int k = (out.count < 8 ? out.count : 8) * 7; k < 56; ++k) rows[lane * kSolRow + k] = 0.0;
+            count_out[s] = out.count;
+            if (status_out) status_out[s] = (uint8_t)out.status;
+        }
+        if (WRITE_SOLS) {
+            __syncwarp();
+            for (int r = 0; r < cnt; ++r) {   // row r -> its solve's 448 B slot: two coalesced stores per row
+                double *dst = sols_out + queue[r] * 56;
+                dst[lane] = rows[r * kSolRow + lane];
+                if (lane < 24) dst[32 + lane] = rows[r * kSolRow + 32 + lane];
+            }
+            __syncwarp();
+        }
+    };
+
+    for (int64_t c = warp; c < n_chunks; c += n_warps) {
+        const int64_t s = c * 32 + lane;
+        bool go = false, dead = false;
+        if (s < total) {
+            Pose P;
+            load_pose(s, n, n_free, free_broadcast, rot9, trans3, free_vals, P);
+            const int verdict = screen_pose(P);
+            go = verdict == 1;
+            dead = !go;
+            if (dead) {
+                count_out[s] = 0;
+                if (status_out) status_out[s] = (uint8_t)(verdict == 2 ? kStatusInvalid : 0);
+            }
+        }
+        const unsigned m_go = __ballot_sync(0xffffffffu, go);
+        if (go) queue[qn + __popc(m_go & lt_mask)] = s;
+        qn += __popc(m_go);
+        if (WRITE_SOLS) {   // zero-fill the rejected solves' slots, row by row, coalesced
+            unsigned m_dead = __ballot_sync(0xffffffffu, dead);
+            while (m_dead) {
+                const int r = __ffs(m_dead) - 1;
+                m_dead &= m_dead - 1;
+                double *dst = sols_out + (c * 32 + r) * 56;
+                dst[lane] = 0.0;
+                if (lane < 24) dst[32 + lane] = 0.0;
+            }
+        }
+        __syncwarp();
+        if (qn >= 32) {
+            solve_batch(32);
+            const int rest = qn - 32;
+            long long carry = 0;
+            if (lane < rest) carry = queue[32 + lane];
+            __syncwarp();
+            if (lane < rest) queue[lane] = carry;
+            __syncwarp();
+            qn = rest;
+        }
+    }
+    if (qn > 0) solve_batch(qn);
+}
+
 // FK (ComputeFk, :307-395): T = prod_k DH_k(q_k), rows k = 0..7 of the Panda modified-DH table.
 __global__ void __launch_bounds__(256)
 fk_kernel(int64_t n, const double *__restrict__ q, double *__restrict__ trans3, double *__restrict__ rot9) {
@@ -118,6 +224,20 @@ fk_kernel(int64_t n, const double *__restrict__ q, double *__restrict__ trans3, 
 cudaError_t launch_ik_batch(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
                             int n_free, int free_broadcast, double *sols_out, int32_t *count_out,
                             uint8_t *status_out, cudaStream_t st) {
+#ifndef TCMP_IK_COMPACT
+#define TCMP_IK_COMPACT 1
+#endif
+#if TCMP_IK_COMPACT
+    if (sols_out) {
+        const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel_compact<true>), ik::kIkBlock, n * n_free);
+        ik::ik_kernel_compact<true><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals,
+                                                                   sols_out, count_out, status_out);
+    } else {
+        const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel_compact<false>), ik::kIkBlock, n * n_free);
+        ik::ik_kernel_compact<false><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals,
+                                                                    sols_out, count_out, status_out);
+    }
+#else
     if (sols_out) {
         const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel<true>), ik::kIkBlock, n * n_free);
         ik::ik_kernel<true><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out,
@@ -127,6 +247,7 @@ cudaError_t launch_ik_batch(int64_t n, const double *rot9, const double *trans3,
         ik::ik_kernel<false><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out,
                                                    count_out, status_out);
     }
+#endif
     return cudaGetLastError();
 }
 
