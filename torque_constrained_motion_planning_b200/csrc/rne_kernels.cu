@@ -6,7 +6,7 @@
 // Data layout: structure-of-arrays [7][n] so that the 32 lanes of a warp read 32 consecutive
 // elements of each joint row (one 256 B request per row per warp, fully coalesced).  Loads are
 // streaming (ld.global.cs) and stores are st.global.cs: every byte is touched exactly once.
-// Bound: FP64 pipe: ~233 B and ~0.8 k FP64 instructions per state.
+// Bound: FP64 pipe: 233 B and ~600 FP64 instructions per state.
 #include "panda_model.cuh"
 #include "tcmp_internal.h"
 
