@@ -414,3 +414,39 @@ def test_forty_million_states_int64_offsets(eng):
     assert np.array_equal(ok[reps - 1, :50_000].cpu().numpy(), ok_o)
     del Q, V, A, M
     torch.cuda.empty_cache()
+
+
+def test_ik_select_sweep_longer_than_a_warp(eng):
+    """n_free = 40 > 32: the select kernel walks the sweep in two rounds and must keep the best across rounds."""
+    from conftest import Q_HI, Q_LO
+    rng = np.random.default_rng(45)
+    n, nf = 600, 40
+    q = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, n))
+    trans, rot = oracle.ref_fk_batch(q)
+    free = np.vstack([rng.uniform(Q_LO[6], Q_HI[6], size=(nf - 1, n)), q[6:7]])     # the exact j7 comes LAST
+    best, cost, nv = eng.ik_select(rot, trans, free, q, 0.0, mode="base", norm="inf")
+    # the pose's own configuration is reachable with cost ~ 0 and lives in the second round
+    assert (cost < 1e-9).all() and np.abs(best - q).max() < 1e-9 and (nv >= 1).all()
+    sols, counts = oracle.ref_ik_batch(rot, trans, free)
+    inside = ((sols >= Q_LO) & (sols <= Q_HI)).all(axis=2) & (np.arange(8)[None, :] < counts[:, None])
+    assert np.array_equal(nv, inside.reshape(n, nf, 8).sum(axis=(1, 2)).astype(np.int32))
+
+
+@pytest.mark.parametrize("mode", ["nov", "dyn"])
+def test_traj_kernel_other_modes(eng, mode):
+    t = load_golden("traj.npz")
+    coeffs = oracle.minjerk_coefficients(t["points"])
+    out = eng.traj_feasibility(coeffs, int(t["n_int"]), float(t["mass"]), mode=mode)
+    tau_o, mask_o, ff_o = oracle.traj_feasibility(mode, t["points"], int(t["n_int"]), float(t["mass"]))
+    assert np.abs(out["tau"].cpu().numpy().T - tau_o).max() < TOL64
+    assert np.array_equal(out["feasible"].cpu().numpy(), mask_o) and out["first_fail"] == ff_o
+
+
+def test_edge_kernel_fp32_path(eng):
+    qa, qb = sample_edges(5000, seed=14)
+    ff_o = oracle.edge_feasibility("rne", qa, qb, 64, 5.0)
+    ff = eng.edge_feasibility(dev(qa.astype(np.float32)), dev(qb.astype(np.float32)), 64, 5.0, mode="rne", dtype="f32")
+    ff = ff.cpu().numpy()
+    # fp32 may move a first failure only where a torque sits within fp32 resolution of a limit
+    assert (ff == ff_o).mean() > 0.995
+    assert np.abs(ff[ff != ff_o] - ff_o[ff != ff_o]).max() <= 64
