@@ -317,28 +317,28 @@ def main():
             ms = float(t.item())
         return ms
 
-    for i in range(W):
-        step(i)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
-    # K steps last ~1 ms, far below nvidia-smi's sampling period: hold the same kernel back to back for
-    # ~1.5 s first so the clock / throttle record (and the `sustained` figure) reflect load, then time K.
-    t_hold = time.perf_counter()
-    held = 0
+        sampler.start()              # covers warm-up, the timed region and the sustained hold below
+    for i in range(W):
+        step(i)
+    ms_total = timed(step, K)        # the contract's number: W warm-up steps, then exactly K timed steps
+    # K steps last ~1 ms, far below nvidia-smi's sampling period: afterwards hold the same step back to back for
+    # ~1.5 s so the clock / throttle record reflects load, and report that rate too (`sustained`).
+    # the step count comes from ms_total (already max-reduced, so identical on every rank: no rank may issue
+    # more collectives than another)
+    held = max(200, int(1.5 / (ms_total / K * 1e-3)) // 200 * 200)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    while time.perf_counter() - t_hold < 1.5:
+    for h in range(0, held, 200):
         for i in range(200):
-            step(held + i)
-        held += 200
+            step(h + i)
         torch.cuda.synchronize()
     if gather is not None:
         gather.join()
     e1.record()
     torch.cuda.synchronize()
     sustained = world * N_STATES * held / (e0.elapsed_time(e1) * 1e-3)
-    ms_total = timed(step, K)
     # kernel-only duration (no collective) for the roofline of the dominant kernel, same stream / events
     ms_kernel = timed(lambda i: engine.torque_test_batch(*sets[i % N_SETS], mode="rne", out_tau=out_tau,
                                                          out_mask=out_mask), K) if world > 1 else ms_total
