@@ -421,8 +421,9 @@ def test_ik_select_sweep_longer_than_a_warp(eng):
     from conftest import Q_HI, Q_LO
     rng = np.random.default_rng(45)
     n, nf = 600, 40
-    q = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, n))
-    trans, rot = oracle.ref_fk_batch(q)
+    q = rng.uniform(Q_LO[:, None] + 1e-6, Q_HI[:, None] - 1e-6, size=(7, n))
+    q[5] = np.minimum(q[5], 3.1)      # the solver returns angles wrapped to (-pi, pi]: joint 6 above pi would come back
+    trans, rot = oracle.ref_fk_batch(q)   # as q - 2 pi, outside its limits, and be filtered like the reference does
     free = np.vstack([rng.uniform(Q_LO[6], Q_HI[6], size=(nf - 1, n)), q[6:7]])     # the exact j7 comes LAST
     best, cost, nv = eng.ik_select(rot, trans, free, q, 0.0, mode="base", norm="inf")
     # the pose's own configuration is reachable with cost ~ 0 and lives in the second round
