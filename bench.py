@@ -147,6 +147,18 @@ def cpu_baseline_run(n_sample, reps, nthreads=0):
     return n_sample * reps / dt, cores, dt
 
 
+def python_port_rate(n=300):
+    """States/s of ONE core running the NumPy restatement that keeps rne.py's per-call structure (np.block 6x6
+    algebra, np.linalg.inv per link): what the reference's own torque test costs on this host."""
+    from oracle import rne_numpy_port as P
+    q, qd, qdd, mass = sample_states(n, seed=2)
+    P.torque_test(q[:, 0], qd[:, 0], qdd[:, 0], mass[0])
+    t0 = time.perf_counter()
+    for i in range(n):
+        P.torque_test(q[:, i], qd[:, i], qdd[:, i], mass[i])
+    return n / (time.perf_counter() - t0)
+
+
 def run_extras(engine, dev, K):
     """IK solves/s (config 3: 1M reachable poses x 25 free values) and RRT* edge checks/s (config 4: 100k edges
     x 64 min-jerk waypoints, rne, 5 kg), device-resident, CUDA-event timed."""
@@ -220,8 +232,10 @@ def run_reference(args):
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d-state seeded subsample of the 1M-state workload per step, C oracle port "
-                                   "of rne.py (the Python reference itself measures ~383 states/s/core, "
-                                   "BASELINE.md section 2)" % n_sample},
+                                   "of rne.py" % n_sample,
+                         "python_port_states_per_s_per_core": python_port_rate(),
+                         "python_port_note": "oracle/rne_numpy_port.py: NumPy restatement at rne.py's own per-call "
+                                             "granularity, 300 states on one core"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -447,8 +461,11 @@ def main():
             v, cores, dt = cpu_baseline_run(N_STATES, 3)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": "3 passes over the same 1M-state workload (%.1f s wall), C oracle port of "
-                                             "rne.py with OpenMP; the Python reference itself measures ~383 "
-                                             "states/s/core (BASELINE.md section 2)" % dt}
+                                             "rne.py with OpenMP" % dt,
+                                   "python_port_states_per_s_per_core": python_port_rate(),
+                                   "python_port_note": "oracle/rne_numpy_port.py: NumPy restatement at rne.py's own "
+                                                       "per-call granularity (np.block / np.linalg.inv per link), "
+                                                       "300 states on one core"}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -136,3 +136,17 @@ def test_ref_ikfast_kats():
     sols, counts = oracle.ref_ik_batch(g["rot"], g["trans"], g["free"])
     assert (counts == g["counts"]).all()
     assert np.abs(sols - g["sols"]).max() < 1e-12
+
+
+def test_numpy_port_at_reference_granularity():
+    """oracle/rne_numpy_port.py (the per-call cost model bench.py times) reproduces the unmodified rne.py."""
+    from oracle import rne_numpy_port as P
+    g = load_golden("states_cfg2.npz")
+    for i in range(60):
+        ok, tau = P.torque_test(g["q"][:, i], g["qd"][:, i], g["qdd"][:, i], g["mass"][i])
+        assert np.abs(tau - g["tau_rne"][:, i]).max() < 1e-12
+        assert ok == bool(g["feasible_rne"][i])
+    k = load_golden("kat_rne.npz")
+    for i in range(k["q"].shape[1]):
+        tau = P.rne(k["q"][:, i], k["qd"][:, i], k["qdd"][:, i], float(k["mass"][i]))
+        assert np.abs(tau - k["tau_raw"][:, i]).max() < 1e-12
