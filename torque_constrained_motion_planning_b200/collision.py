@@ -97,16 +97,18 @@ def get_collision_fn(body=None, joints=None, obstacles=(), attachments=(), self_
     obstacles = list(obstacles)
     if backend == "cuda":
         from . import engine
+        packed = engine.PackedScene(obstacles, lower, upper, payload_radius)   # marshalled once per scene
 
         def batch_cuda(qs):
             qs = np.atleast_2d(np.asarray(qs, dtype=float))
-            hit = engine.collision_batch(np.ascontiguousarray(qs[:, :7].T), obstacles, lower, upper, payload_radius)
+            hit = engine.collision_batch(np.ascontiguousarray(qs[:, :7].T), packed)
             return hit.astype(bool)
 
         def collision_cuda(q, verbose=False):
             return bool(batch_cuda([q])[0])
         collision_cuda.batch = batch_cuda
-        collision_cuda.scene = {"obstacles": obstacles, "q_lo": lower, "q_hi": upper, "payload_radius": payload_radius}
+        collision_cuda.scene = {"obstacles": obstacles, "q_lo": lower, "q_hi": upper, "payload_radius": payload_radius,
+                                "packed": packed}
         return collision_cuda
 
     def batch(qs):

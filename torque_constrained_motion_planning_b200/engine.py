@@ -300,6 +300,17 @@ class _Obstacle(ctypes.Structure):   # tcmp_obstacle (include/tcmp.h)
                 ("half", ctypes.c_double * 3)]
 
 
+class PackedScene:
+    """Obstacles + joint limits marshalled once (ctypes array of tcmp_obstacle, contiguous limit arrays) so that
+    per-edge calls do not rebuild them (that was half of a 200 us collision call in the planner)."""
+
+    def __init__(self, obstacles, q_lo=None, q_hi=None, payload_radius=0.0):
+        self.n = len(obstacles)
+        self.obs = pack_obstacles(obstacles)
+        self.lo, self.hi = _limits_arrays(q_lo, q_hi)
+        self.payload_radius = float(payload_radius)
+
+
 def pack_obstacles(obstacles):
     """collision.Box / collision.Sphere objects -> ctypes array of tcmp_obstacle."""
     arr = (_Obstacle * max(len(obstacles), 1))()
@@ -324,19 +335,20 @@ def _limits_arrays(q_lo, q_hi):
 
 
 def collision_batch(q, obstacles, q_lo=None, q_hi=None, payload_radius: float = 0.0):
-    """Synthetic-scene collision predicate (tcmp_collision_batch): q ``[7][n]`` -> hit uint8 ``[n]``."""
+    """Synthetic-scene collision predicate (tcmp_collision_batch): q ``[7][n]`` -> hit uint8 ``[n]``.
+    ``obstacles`` is a list of collision.Box / Sphere or a :class:`PackedScene` (then the other arguments are
+    taken from it)."""
     torch = _torch()
     lib = load()
-    lo, hi = _limits_arrays(q_lo, q_hi)
+    sc = obstacles if isinstance(obstacles, PackedScene) else PackedScene(obstacles, q_lo, q_hi, payload_radius)
     host = not _is_cuda_tensor(q)
     dev = torch.device("cuda", torch.cuda.current_device()) if host else q.device
     n = int(q.shape[1])
-    obs = pack_obstacles(obstacles)
     with torch.cuda.device(dev):
         qt = _as_dev(q, "f64", (7, n), dev)
         hit = torch.empty((n,), dtype=torch.uint8, device=dev)
-        check(lib.tcmp_collision_batch(n, _ptr(qt), len(obstacles), ctypes.addressof(obs), _nptr(lo), _nptr(hi),
-                                       float(payload_radius), _ptr(hit), _stream_ptr()))
+        check(lib.tcmp_collision_batch(n, _ptr(qt), sc.n, ctypes.addressof(sc.obs), _nptr(sc.lo), _nptr(sc.hi),
+                                       sc.payload_radius, _ptr(hit), _stream_ptr()))
     return hit.cpu().numpy() if host else hit
 
 
@@ -347,19 +359,18 @@ def extend_prefix(q1, q2, resolution, obstacles, payload_mass: float = 0.0, mode
     q1/q2 ``[7][n_edges]`` -> (n_steps int32 [n_edges], prefix int32 [n_edges])."""
     torch = _torch()
     lib = load()
-    lo, hi = _limits_arrays(q_lo, q_hi)
+    sc = obstacles if isinstance(obstacles, PackedScene) else PackedScene(obstacles, q_lo, q_hi, payload_radius)
     res = np.ascontiguousarray(resolution, dtype=np.float64)
     host = not _is_cuda_tensor(q1)
     dev = torch.device("cuda", torch.cuda.current_device()) if host else q1.device
     n = int(q1.shape[1])
-    obs = pack_obstacles(obstacles)
     with torch.cuda.device(dev):
         a = _as_dev(q1, "f64", (7, n), dev)
         b = _as_dev(q2, "f64", (7, n), dev)
         ns = torch.empty((n,), dtype=torch.int32, device=dev)
         pre = torch.empty((n,), dtype=torch.int32, device=dev)
-        check(lib.tcmp_extend_prefix(MODE[mode], n, _ptr(a), _ptr(b), _nptr(res), len(obstacles),
-                                     ctypes.addressof(obs), _nptr(lo), _nptr(hi), float(payload_radius),
+        check(lib.tcmp_extend_prefix(MODE[mode], n, _ptr(a), _ptr(b), _nptr(res), sc.n,
+                                     ctypes.addressof(sc.obs), _nptr(sc.lo), _nptr(sc.hi), sc.payload_radius,
                                      float(payload_mass), float(payload_threshold), _ptr(ns), _ptr(pre),
                                      _stream_ptr()))
     if host:

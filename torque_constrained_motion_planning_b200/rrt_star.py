@@ -239,8 +239,9 @@ def rrt_star_force_aware_batched(start, goal, distance_weights, sample, resoluti
         near = d2.argmin(axis=1)
         q1 = C[near]
         ns, pre = engine.extend_prefix(np.ascontiguousarray(q1.T), np.ascontiguousarray(targets.T), res,
-                                       scene["obstacles"], torque_fn.mass(), mode=torque_fn.mode,
-                                       q_lo=scene["q_lo"], q_hi=scene["q_hi"], payload_radius=scene["payload_radius"])
+                                       scene.get("packed") or scene["obstacles"], torque_fn.mass(),
+                                       mode=torque_fn.mode, q_lo=scene["q_lo"], q_hi=scene["q_hi"],
+                                       payload_radius=scene["payload_radius"])
         for b in range(batch):
             if pre[b] == 0:
                 continue
