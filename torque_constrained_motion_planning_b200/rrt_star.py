@@ -100,10 +100,37 @@ def _first_failure(flags_bad):
     return int(np.argmax(flags_bad)) if flags_bad.any() else len(flags_bad)
 
 
+def _fused_prefix(sequence, collision, torque):
+    """One launch for the whole edge when everything needed is on hand: an ExtendSequence (end points +
+    resolutions, 2-norm), a CUDA-backed collision predicate (its packed scene) and a torque test from
+    panda_primitives (mode + payload).  tcmp_extend_prefix regenerates the same configurations on the device,
+    checks collision first and the static torque test only for collision-free ones, and returns the length of
+    the safe prefix -- identical to the loop below (tests/test_gpu_parity.py).  Returns None when not applicable."""
+    scene = getattr(collision, "scene", None)
+    if scene is None or "packed" not in scene or not hasattr(torque, "mode") or not hasattr(sequence, "q1"):
+        return None
+    if getattr(sequence, "norm", None) != 2:
+        return None
+    from . import engine
+    q1 = np.asarray(sequence.q1, dtype=float).reshape(7, 1)
+    q2 = np.asarray(sequence.q2, dtype=float).reshape(7, 1)
+    _, pre = engine.extend_prefix(q1, q2, sequence.resolutions, scene["packed"], torque.mass(), mode=torque.mode)
+    keep = int(pre[0])
+    out = []
+    for q in sequence:
+        if len(out) == keep:
+            break
+        out.append(q)
+    return out
+
+
 def safe_path_force_aware(sequence, collision, torque):
     """Longest prefix of ``sequence`` whose configurations are collision-free AND within torque limits
     (rrt_star.py:90-98).  Batched when both predicates offer ``.batch``; the torque test is never evaluated
     at or beyond the first collision, exactly like the reference's short-circuit."""
+    fused = _fused_prefix(sequence, collision, torque)
+    if fused is not None:
+        return fused
     configs = list(sequence)
     if not configs:
         return configs

@@ -100,13 +100,28 @@ def get_refine_fn(body, joints, num_steps=0):
     return fn
 
 
+class ExtendSequence:
+    """The iterable utils.get_extend_fn returns: iterating it yields exactly the reference's configurations
+    (utils.py:3031-3041,3068-3077), and it also remembers its end points and resolutions so that
+    rrt_star.safe_path_force_aware can hand the WHOLE edge to the fused kernel (tcmp_extend_prefix) instead of
+    materialising it first."""
+
+    def __init__(self, q1, q2, resolutions, norm, body, joints):
+        self.q1, self.q2, self.resolutions, self.norm = q1, q2, resolutions, norm
+        self._body, self._joints = body, joints
+
+    def __iter__(self):
+        steps = int(np.linalg.norm(np.divide(np.asarray(self.q2) - np.asarray(self.q1), self.resolutions),
+                                   ord=self.norm))
+        return get_refine_fn(self._body, self._joints, num_steps=steps)(self.q1, self.q2)
+
+
 def get_extend_fn(body, joints, resolutions=None, norm=2):
     """utils.py:3068-3077: steps = int(|| (q2 - q1) / resolutions ||_norm)."""
     res = DEFAULT_RESOLUTION * np.ones(len(joints)) if resolutions is None else np.asarray(resolutions, dtype=float)
 
     def fn(q1, q2):
-        steps = int(np.linalg.norm(np.divide(np.asarray(q2) - np.asarray(q1), res), ord=norm))
-        return get_refine_fn(body, joints, num_steps=steps)(q1, q2)
+        return ExtendSequence(q1, q2, res, norm, body, joints)
     return fn
 
 
