@@ -62,6 +62,8 @@ def main():
         pp.planner_fn_force_aware(tuple(Q_HOME), pose, problem())          # warm-up (context, first launches)
         t_strict, traj = timed(lambda: pp.planner_fn_force_aware(tuple(Q_HOME), pose, problem()), 3)
         t_batched, traj_b = timed(lambda: pp.planner_fn_force_aware(tuple(Q_HOME), pose, problem(), batch=32), 3)
+        t_arrays, _ = timed(lambda: pp.planner_fn_force_aware(tuple(Q_HOME), pose, problem(), batch=32,
+                                                              as_arrays=True), 3)
 
         # CPU arm: same planner, serial per-state predicates
         calls = {"torque": 0}
@@ -102,7 +104,7 @@ def main():
                 np.allclose(np.array([c_.values for c_ in traj.path]), np.array(out_cpu[0]), rtol=0, atol=1e-12))
         print(json.dumps({
             "scene": name, "samples": None if traj is None else len(traj.path),
-            "gpu_strict_s": t_strict, "gpu_batched_s": t_batched,
+            "gpu_strict_s": t_strict, "gpu_batched_s": t_batched, "gpu_batched_arrays_s": t_arrays,
             "gpu_batched_samples": None if traj_b is None else len(traj_b.path),
             "cpu_serial_s": t_cpu, "cpu_torque_calls": n_calls,
             "python_reference_estimate_s": n_calls * 2.6e-3,

@@ -179,6 +179,13 @@ def test_planner_fn_force_aware_end_to_end(mode, mass):
     # determinism under fixed seeds
     traj2 = run()
     assert np.array_equal(np.array([c_.values for c_ in traj2.path]).T, q)
+    # array-returning form: same numbers, no per-sample objects
+    random.seed(3)
+    np.random.seed(3)
+    arr = pp.planner_fn_force_aware(start, pose, utils.Problem(None, scene, "coke", mass, 2, mode), as_arrays=True)
+    assert set(arr) == {"q", "qd", "qdd", "torques", "ts"}
+    assert np.array_equal(arr["q"].T, q) and np.array_equal(arr["qd"].T, qd)
+    assert np.abs(arr["torques"].T - tau0).max() < 1e-9
 
 
 def test_batched_speculative_planner_returns_valid_trajectory():

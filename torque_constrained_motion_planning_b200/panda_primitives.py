@@ -140,17 +140,21 @@ def get_dynamics_fn_v5(problem, resolutions):
 
     def fused_check(path, torque_fn, want_log_torques=False):
         """Samples of the min-jerk trajectory AND their torque test in one kernel launch
-        (tcmp_traj_feasibility).  Returns dict(path, vels, accels, psg, feasible, first_fail, tau)."""
+        (tcmp_traj_feasibility).  Returns dict(path, vels, accels, psg, feasible, first_fail, tau).  With
+        ``dynam_fn.as_arrays = True`` path / vels / accels / psg are NumPy arrays [n][7] instead of the nested
+        lists the reference's callers expect (list construction is most of a plan's wall time)."""
         m_coeff, move_time, num_intervals = _plan(path)
         mode = getattr(torque_fn, "mode", "rne")
         mass = torque_fn.mass() if hasattr(torque_fn, "mass") else 0.0
         out = engine.traj_feasibility(coefficients_for_kernel(m_coeff), num_intervals, mass, mode=mode)
         n = out["feasible"].shape[0]
         q = out["q"].T.cpu().numpy()
+        arrays = getattr(dynam_fn, "as_arrays", False)
+        conv = (lambda a: a) if arrays else (lambda a: a.tolist())
         res = {
-            "path": q.tolist(), "vels": out["qd"].T.cpu().numpy().tolist(),
-            "accels": out["qdd"].T.cpu().numpy().tolist(),
-            "psg": [move_time * i / n for i in range(n)],
+            "path": conv(q), "vels": conv(out["qd"].T.cpu().numpy()),
+            "accels": conv(out["qdd"].T.cpu().numpy()),
+            "psg": move_time * np.arange(n) / n if arrays else [move_time * i / n for i in range(n)],
             "feasible": out["first_fail"] == n, "first_fail": out["first_fail"],
             "tau": out["tau"].T.cpu().numpy(),
         }
@@ -217,10 +221,12 @@ def bi_panda_inverse_kinematics(robot, arm, gripper_link, gripper_pose, max_atte
     return None
 
 
-def planner_fn_force_aware(start_conf, pose, problem, batch=0, collision_backend="cuda"):
+def planner_fn_force_aware(start_conf, pose, problem, batch=0, collision_backend="cuda", as_arrays=False):
     """panda_primitives.py:223-282.  Returns a Trajectory (``.path[i].values / .velocities / .accelerations /
     .dt / .torques``) or None.  Extra keyword arguments (defaults keep the reference's behaviour):
-    ``batch`` > 0 = speculative batched tree growth; ``collision_backend`` "cuda" | "numpy"."""
+    ``batch`` > 0 = speculative batched tree growth; ``collision_backend`` "cuda" | "numpy"; ``as_arrays`` = return
+    ``dict(q, qd, qdd, torques, ts)`` of NumPy arrays (the .npz schema of collect_data.py:109-131) instead of
+    building one Conf object per sample."""
     timestamp = "{}_{}".format(*str(datetime.datetime.now()).split(" "))
     robot = problem.robot
     obstacles = problem.fixed
@@ -230,6 +236,7 @@ def planner_fn_force_aware(start_conf, pose, problem, batch=0, collision_backend
     arm_joints = get_arm_joints(robot)
     resolutions = 0.2 ** np.ones(len(arm_joints))
     dynam_fn = get_dynamics_fn_v5(problem, resolutions)
+    dynam_fn.as_arrays = bool(as_arrays)
     grasp = getattr(problem.payload, "grasp", None)
     gripper_pose = pose if grasp is None else grasp(pose)
     collision_fn = get_collision_fn(robot, arm_joints, obstacles, self_collisions=SELF_COLLISIONS,
@@ -257,5 +264,8 @@ def planner_fn_force_aware(start_conf, pose, problem, batch=0, collision_backend
         return None
     # torques logged per sample by Conf (utils.py:3376-3378): rne without payload, batched in one launch
     log_tau = _rne_mod.rne_batch(_soa(approach_path), _soa(approach_vels), _soa(approach_accels), 0.0).T
+    if as_arrays:
+        return {"q": np.asarray(approach_path), "qd": np.asarray(approach_vels), "qdd": np.asarray(approach_accels),
+                "torques": log_tau, "ts": np.asarray(approach_dts)}
     return create_trajectory(robot, arm_joints, approach_path, bodies=[problem.payload], velocities=approach_vels,
                              accelerations=approach_accels, dts=approach_dts, ts=timestamp, torques=log_tau)
