@@ -27,9 +27,18 @@
 // loops halves the SASS (140 KB -> 72 KB) but is 15 % SLOWER (call ABI + 432 B of local stack), so everything
 // stays inlined; define TCMP_OUTLINE as __noinline__ to reproduce.
 #define TCMP_OUTLINE
+#ifndef TCMP_IK_UNROLL
+#define TCMP_IK_UNROLL 1
+#endif
+#if TCMP_IK_UNROLL
+#define TCMP_ROOT_LOOP
+#else
+#define TCMP_ROOT_LOOP _Pragma("unroll 1")
+#endif
 #else
 #define TCMP_HD
 #define TCMP_OUTLINE
+#define TCMP_ROOT_LOOP
 #endif
 
 namespace tcmp {
@@ -152,6 +161,7 @@ TCMP_HD TCMP_OUTLINE inline void solve_shoulder(const Pose &P, const Root &j3, c
     }
     if (j1ok[0] && j1ok[1] && same_root(j1r[0], j1r[1])) j1ok[1] = false;
 
+TCMP_ROOT_LOOP
     for (int i1 = 0; i1 < 2; ++i1) {
         if (!j1ok[i1]) continue;
         const double j1 = j1r[i1].a, s1 = j1r[i1].s, c1 = j1r[i1].c;
@@ -274,6 +284,7 @@ TCMP_HD inline void solve_one(const Pose &P, Emit &out) {
     Root j3r[2] = {make_root(1.10379390314189 + a3), make_root(4.24538655673168 - a3)};
     bool j3ok[2] = {true, !same_root(j3r[0], j3r[1])};
 
+TCMP_ROOT_LOOP
     for (int i3 = 0; i3 < 2; ++i3) {
         if (!j3ok[i3]) continue;
         const Root &j3 = j3r[i3];
@@ -300,6 +311,7 @@ TCMP_HD inline void solve_one(const Pose &P, Emit &out) {
         Root j5r[2] = {make_root(-a5 - at5), make_root(3.14159265358979 + a5 - at5)};
         bool j5ok[2] = {true, !same_root(j5r[0], j5r[1])};
 
+TCMP_ROOT_LOOP
         for (int i5 = 0; i5 < 2; ++i5) {
             if (!j5ok[i5]) continue;
             const Root &j5 = j5r[i5];
