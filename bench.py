@@ -418,9 +418,31 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * N_STATES * K / e2e_s
+
     # sanity: the host path and the device path agree bit for bit on the same inputs
     tau_d, ok_d = engine.torque_test_batch(*sets[0], mode="rne")
     assert torch.equal(tau_d.cpu(), htau) and torch.equal(ok_d.cpu(), hok)
+
+    # what bounds it: the same call without the torque read-back (the planner's predicate needs the mask only), and
+    # a plain pinned cudaMemcpy of one input array in each direction (the PCIe ceiling of this box, this run)
+    def timed_host(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        t_ = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t_) / reps
+    mask_only_s = timed_host(lambda: engine.torque_test_batch_host_into(ws, "rne", "f64", nq, nqd, nqdd, nm, 0.0, 0.01,
+                                                                       None, nok), max(3, K // 2))
+    dq = torch.empty((7, N_STATES), dtype=torch.float64, device=dev)
+    h2d_s = timed_host(lambda: dq.copy_(hq, non_blocking=True), 10)
+    d2h_s = timed_host(lambda: htau.copy_(dq, non_blocking=True), 10)
+    link = {"h2d_gbs_in_call": N_STATES * 176 / (e2e_s / K) / 1e9, "h2d_gbs_in_call_mask_only": N_STATES * 176 / mask_only_s / 1e9,
+            "h2d_gbs_plain_memcpy": N_STATES * 56 / h2d_s / 1e9, "d2h_gbs_plain_memcpy": N_STATES * 56 / d2h_s / 1e9,
+            "mask_only_states_per_s": N_STATES / mask_only_s,
+            "note": "per rank; the call moves 176 B/state host->device, so PCIe bounds it at plain-memcpy GB/s / 176 B"}
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -435,9 +457,9 @@ def main():
                 "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                 "frac": achieved_tf / (fp64_peak / 1e12),
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, from the ncu --set full
-                # capture in profiles/r01/ncu_full_rne_batch_kernel_raw.csv (168.0 MB read + 26.0 MB written at
+                # capture in profiles/r01/ncu_full_rne_batch_kernel_final_raw.csv (168.0 MB read + 26.8 MB written at
                 # kernel end; the remaining dirty lines are still in the 126 MB L2) -- <= 233 MB algorithmic
-                "traffic": 194.0e6,
+                "traffic": 194.8e6,
                 "peak_source": "tcmp_fp64_peak DFMA microbenchmark measured in this run (MEASURED_PEAKS.json "
                                "carries no FP64 entry; datasheet 37.2 TFLOP/s)",
                 "flops_per_state": FLOPS_PER_STATE, "kernel": "rne_batch_kernel<double,DYN,!TOOL,tau,mask>",
@@ -453,7 +475,8 @@ def main():
                           "note": "same step held back to back for >= 1.5 s (device-timed); clocks sampled over it"},
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(N_STATES * 176), "d2h_bytes_per_step": int(N_STATES * 57),
-                    "api": "tcmp_rne_batch_host (pinned host SoA arrays, 3-stage chunked H2D/kernel/D2H pipeline)"},
+                    "api": "tcmp_rne_batch_host (pinned host SoA arrays, 3-stage chunked H2D/kernel/D2H pipeline)",
+                    "link": link},
             "gpu_launches": K,
             "clocks": clocks,
         }

@@ -41,6 +41,26 @@ def test_config2_one_million_states(eng, mode):
     assert np.array_equal(ok_h, ok_o) and np.abs(tau_h - tau_o).max() < 1e-9
 
 
+def test_states_beyond_int32_offsets(eng):
+    """K1 indexes with 32-bit offsets while 7*n fits 31 bits and with 64-bit ones above (rne_kernels.cu
+    launch_indexed).  320M static states (7*n = 2.24e9 > 2^31) made of a repeated 1M block: the 64-bit path must
+    reproduce, block after block, the masks the 32-bit path gives for the block alone."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    reps, n = 320, 1_000_000
+    if free < 7 * reps * n * 8 * 1.2:
+        pytest.skip("needs 22 GB of free HBM")
+    q, _, _, mass = sample_states(n, seed=7)
+    _, ok_block = eng.torque_test_batch(dev(q), None, None, dev(mass), mode="nov")
+    big_q = dev(q).repeat(1, reps)
+    big_m = dev(mass).repeat(reps)
+    ok = torch.empty(reps * n, dtype=torch.uint8, device="cuda")
+    eng.torque_test_batch(big_q, None, None, big_m, mode="nov", out_mask=ok, want_tau=False)
+    assert torch.equal(ok.view(reps, n), ok_block.view(1, n).expand(reps, n).to(ok.dtype))
+    _, ok_o = oracle.torque_test_batch("nov", q, None, None, mass, nthreads=NT)
+    assert np.array_equal(ok_block.cpu().numpy().astype(bool), ok_o.astype(bool))
+
+
 def test_config3_one_million_poses_times_25(eng):
     """configs[2]: 1M reachable poses x 25 free values (own j7 first, then uniform) -- solution COUNT bit-exact on all
     25M solves against the compiled, unmodified reference; values checked on a slice."""

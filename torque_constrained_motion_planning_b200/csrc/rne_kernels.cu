@@ -31,6 +31,9 @@ __device__ __forceinline__ void prefetch_line(const void *p) {
 #ifndef TCMP_PDL
 #define TCMP_PDL 1
 #endif
+#ifndef TCMP_INT_INDEX
+#define TCMP_INT_INDEX 1
+#endif
 #ifndef TCMP_DOUBLE_BUFFER
 #define TCMP_DOUBLE_BUFFER 1   // measured +3..5 % with 3 resident CTAs (168 registers, no spills)
 #endif
@@ -55,9 +58,11 @@ struct MaskDests {
 #else
 #define TCMP_RNE_BOUNDS TCMP_RNE_BLOCK
 #endif
-template <typename T, bool DYN, bool TOOL, bool WRITE_TAU, bool WRITE_MASK, bool SCATTER = false>
+// I: element-index type.  int when every offset j*n + i (and the grid-stride overshoot) fits 31 bits -- one
+// IMAD.WIDE per address instead of 64-bit multiply-add chains -- else int64_t.
+template <typename T, typename I, bool DYN, bool TOOL, bool WRITE_TAU, bool WRITE_MASK, bool SCATTER = false>
 __global__ void __launch_bounds__(TCMP_RNE_BOUNDS)
-rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, const T *__restrict__ qdd,
+rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T *__restrict__ qdd,
                  const T *__restrict__ payload_mass, T payload_scalar, T payload_threshold,
                  T *__restrict__ tau_out, uint8_t *__restrict__ feasible_out, MaskDests dests) {
 #if TCMP_PDL
@@ -73,10 +78,10 @@ rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, c
     // recursion starts, so a warp never sits in a long-scoreboard stall with nothing to issue (ncu: 1.06 -> 0.14
     // long-scoreboard stalls per issue).  TCMP_DOUBLE_BUFFER == 2 ping-pongs two register sets (loop unrolled
     // twice) instead of copying next -> current after every state.
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const I stride = (I)(gridDim.x * blockDim.x);
+    I i = (I)(blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= n) return;
-    auto load = [&](int64_t at, T (&lq)[7], T (&lv)[7], T (&la)[7], T &lm) {
+    auto load = [&](I at, T (&lq)[7], T (&lv)[7], T (&la)[7], T &lm) {
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
             lq[j] = __ldcs(q + j * n + at);
@@ -84,7 +89,7 @@ rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, c
         }
         lm = payload_mass ? __ldcs(payload_mass + at) : payload_scalar;
     };
-    auto consume = [&](int64_t at, const T (&lq)[7], const T (&lv)[7], const T (&la)[7], T lm) {
+    auto consume = [&](I at, const T (&lq)[7], const T (&lv)[7], const T (&la)[7], T lm) {
         T tau[7];
         const T mp_inertial = TOOL ? T(0) : (lm > payload_threshold ? lm : T(0));
         const T mp_tool = TOOL ? lm : T(0);
@@ -106,7 +111,7 @@ rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, c
     load(i, qa, va, aa, ma);
 #if TCMP_DOUBLE_BUFFER == 2
     for (;;) {
-        int64_t nx = i + stride;
+        I nx = i + stride;
         bool more = nx < n;
         if (more) load(nx, qb, vb, ab, mb);
         consume(i, qa, va, aa, ma);
@@ -121,7 +126,7 @@ rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, c
     }
 #else
     for (;;) {
-        const int64_t nx = i + stride;
+        const I nx = i + stride;
         const bool more = nx < n;
         if (more) load(nx, qb, vb, ab, mb);
         consume(i, qa, va, aa, ma);
@@ -137,15 +142,15 @@ rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, c
 #endif
 }
 #else
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const I stride = (I)(gridDim.x * blockDim.x);
+    for (I i = (I)(blockIdx.x * blockDim.x + threadIdx.x); i < n; i += stride) {
         T qs[7], vs[7], as[7], tau[7];
 #if TCMP_PREFETCH
         // ncu (round 1): 0.92 long-scoreboard stalls per issued instruction -- each state starts by waiting
         // ~800 cycles for its 22 DRAM loads with only ~3 warps per scheduler to cover them.  Prefetching the
         // NEXT state's rows while this one computes costs no registers and turns those loads into cache hits.
         {
-            const int64_t nx = i + stride;
+            const I nx = i + stride;
             if (nx < n) {
 #pragma unroll
                 for (int j = 0; j < 7; ++j) {
@@ -189,10 +194,13 @@ rne_batch_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, c
 }
 #endif
 
-template <typename T, bool DYN, bool TOOL, bool WT, bool WM>
-static cudaError_t launch_one(int64_t n, const void *q, const void *qd, const void *qdd, const void *pm,
-                              double ps, double pt, void *tau, uint8_t *mask, cudaStream_t st) {
-    auto kern = rne_batch_kernel<T, DYN, TOOL, WT, WM>;
+// 31-bit offsets (7 rows of n elements plus the grid-stride overshoot of at most one grid) -> int indices
+static inline bool fits_int(int64_t n) { return n < (int64_t)(0x7fffffff / 7) - 148 * 32 * 2048; }
+
+template <typename T, typename I, bool DYN, bool TOOL, bool WT, bool WM, bool SC>
+static cudaError_t launch_kernel(int64_t n, const void *q, const void *qd, const void *qdd, const void *pm, double ps,
+                                 double pt, void *tau, uint8_t *mask, const MaskDests &dests, cudaStream_t st) {
+    auto kern = rne_batch_kernel<T, I, DYN, TOOL, WT, WM, SC>;
     const int grid = grid_for(reinterpret_cast<const void *>(kern), TCMP_RNE_BLOCK, n);
 #if TCMP_PDL
     cudaLaunchConfig_t cfg = {};
@@ -204,13 +212,28 @@ static cudaError_t launch_one(int64_t n, const void *q, const void *qd, const vo
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, n, (const T *)q, (const T *)qd, (const T *)qdd, (const T *)pm, (T)ps, (T)pt,
-                              (T *)tau, mask, MaskDests());
+    return cudaLaunchKernelEx(&cfg, kern, (I)n, (const T *)q, (const T *)qd, (const T *)qdd, (const T *)pm, (T)ps,
+                              (T)pt, (T *)tau, mask, dests);
 #else
-    kern<<<grid, TCMP_RNE_BLOCK, 0, st>>>(n, (const T *)q, (const T *)qd, (const T *)qdd, (const T *)pm, (T)ps, (T)pt,
-                                          (T *)tau, mask, MaskDests());
+    kern<<<grid, TCMP_RNE_BLOCK, 0, st>>>((I)n, (const T *)q, (const T *)qd, (const T *)qdd, (const T *)pm, (T)ps,
+                                          (T)pt, (T *)tau, mask, dests);
     return cudaGetLastError();
 #endif
+}
+
+template <typename T, bool DYN, bool TOOL, bool WT, bool WM, bool SC>
+static cudaError_t launch_indexed(int64_t n, const void *q, const void *qd, const void *qdd, const void *pm, double ps,
+                                  double pt, void *tau, uint8_t *mask, const MaskDests &dests, cudaStream_t st) {
+#if TCMP_INT_INDEX
+    if (fits_int(n)) return launch_kernel<T, int, DYN, TOOL, WT, WM, SC>(n, q, qd, qdd, pm, ps, pt, tau, mask, dests, st);
+#endif
+    return launch_kernel<T, int64_t, DYN, TOOL, WT, WM, SC>(n, q, qd, qdd, pm, ps, pt, tau, mask, dests, st);
+}
+
+template <typename T, bool DYN, bool TOOL, bool WT, bool WM>
+static cudaError_t launch_one(int64_t n, const void *q, const void *qd, const void *qdd, const void *pm,
+                              double ps, double pt, void *tau, uint8_t *mask, cudaStream_t st) {
+    return launch_indexed<T, DYN, TOOL, WT, WM, false>(n, q, qd, qdd, pm, ps, pt, tau, mask, MaskDests(), st);
 }
 
 template <typename T, bool DYN, bool TOOL>
@@ -255,18 +278,8 @@ cudaError_t launch_rne_batch(int mode, int dtype, int64_t n, const void *q, cons
 template <typename T, bool DYN, bool TOOL>
 static cudaError_t launch_scatter_t(int64_t n, const void *q, const void *qd, const void *qdd, const void *pm,
                                     double ps, double pt, void *tau, const MaskDests &dests, cudaStream_t st) {
-    if (tau) {
-        auto kern = rne_batch_kernel<T, DYN, TOOL, true, true, true>;
-        const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, n);
-        kern<<<grid, 128, 0, st>>>(n, (const T *)q, (const T *)qd, (const T *)qdd, (const T *)pm, (T)ps, (T)pt,
-                                   (T *)tau, nullptr, dests);
-    } else {
-        auto kern = rne_batch_kernel<T, DYN, TOOL, false, true, true>;
-        const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, n);
-        kern<<<grid, 128, 0, st>>>(n, (const T *)q, (const T *)qd, (const T *)qdd, (const T *)pm, (T)ps, (T)pt,
-                                   (T *)tau, nullptr, dests);
-    }
-    return cudaGetLastError();
+    if (tau) return launch_indexed<T, DYN, TOOL, true, true, true>(n, q, qd, qdd, pm, ps, pt, tau, nullptr, dests, st);
+    return launch_indexed<T, DYN, TOOL, false, true, true>(n, q, qd, qdd, pm, ps, pt, tau, nullptr, dests, st);
 }
 
 cudaError_t launch_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,

@@ -89,6 +89,40 @@ struct tcmp_workspace {
     int device = 0;
 };
 
+// A workspace belongs to the device that was current when it was created; host-array calls made while another
+// device is current switch to it for the duration of the call.
+struct DeviceScope {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceScope(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceScope() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceScope(const DeviceScope &) = delete;
+    DeviceScope &operator=(const DeviceScope &) = delete;
+};
+
+// Drain the stage streams; used on the success path and before reporting a mid-pipeline failure so no copy into
+// caller memory is still in flight when the call returns.
+static cudaError_t ws_drain(tcmp_workspace *ws) {
+    cudaError_t first = cudaSuccess;
+    for (int s = 0; s < tcmp_workspace::kStages; ++s) {
+        cudaError_t e = cudaStreamSynchronize(ws->stream[s]);
+        if (first == cudaSuccess) first = e;
+    }
+    return first;
+}
+#define TCMP_CUDA_WS(ws, expr)                  \
+    do {                                        \
+        cudaError_t e__ = (expr);               \
+        if (e__ != cudaSuccess) {               \
+            ws_drain(ws);                       \
+            return cuda_fail(e__, #expr);       \
+        }                                       \
+    } while (0)
+
 static int ws_reserve(tcmp_workspace *ws, size_t bytes_per_stage) {
     if (bytes_per_stage <= ws->bytes) return TCMP_OK;
     for (int s = 0; s < tcmp_workspace::kStages; ++s) {
@@ -310,6 +344,7 @@ int tcmp_workspace_create(tcmp_workspace **out, int64_t chunk_states) {
 
 int tcmp_workspace_destroy(tcmp_workspace *ws) {
     if (!ws) return TCMP_OK;
+    DeviceScope scope(ws->device);
     for (int s = 0; s < tcmp_workspace::kStages; ++s) {
         if (ws->stream[s]) {
             cudaStreamSynchronize(ws->stream[s]);
@@ -338,6 +373,7 @@ int tcmp_rne_batch_host(tcmp_workspace *ws, int mode, int dtype, int64_t n, cons
                         const void *qdd, const void *payload_mass, double payload_scalar, double payload_threshold,
                         void *tau_out, uint8_t *feasible_out) {
     if (!ws) return fail(TCMP_ERR_INVALID_ARG, "workspace is NULL");
+    DeviceScope scope(ws->device);
     if (int rc = check_common(mode, dtype, n)) return rc;
     if (n == 0) return TCMP_OK;
     if (!q && mode != TCMP_MODE_BASE) return fail(TCMP_ERR_INVALID_ARG, "q is NULL");
@@ -357,20 +393,20 @@ int tcmp_rne_batch_host(tcmp_workspace *ws, int mode, int dtype, int64_t n, cons
         char *dq = base, *dqd = base + 7 * row, *dqdd = base + 14 * row, *dm = base + 21 * row, *dtau = base + 22 * row;
         uint8_t *dmask = (uint8_t *)(base + 29 * row);
         // the tile is dense [7][len]: the kernel sees n == len
-        if (q) TCMP_CUDA(h2d_rows(dq, q, 7, n, off, len, esz, st));
+        if (q) TCMP_CUDA_WS(ws, h2d_rows(dq, q, 7, n, off, len, esz, st));
         if (qd && mode != TCMP_MODE_NOV) {
-            TCMP_CUDA(h2d_rows(dqd, qd, 7, n, off, len, esz, st));
-            TCMP_CUDA(h2d_rows(dqdd, qdd, 7, n, off, len, esz, st));
+            TCMP_CUDA_WS(ws, h2d_rows(dqd, qd, 7, n, off, len, esz, st));
+            TCMP_CUDA_WS(ws, h2d_rows(dqdd, qdd, 7, n, off, len, esz, st));
         }
-        if (payload_mass) TCMP_CUDA(h2d_rows(dm, payload_mass, 1, n, off, len, esz, st));
+        if (payload_mass) TCMP_CUDA_WS(ws, h2d_rows(dm, payload_mass, 1, n, off, len, esz, st));
         const bool dyn_in = qd && mode != TCMP_MODE_NOV;
-        TCMP_CUDA(launch_rne_batch(mode, dtype, len, dq, dyn_in ? dqd : nullptr, dyn_in ? dqdd : nullptr,
+        TCMP_CUDA_WS(ws, launch_rne_batch(mode, dtype, len, dq, dyn_in ? dqd : nullptr, dyn_in ? dqdd : nullptr,
                                    payload_mass ? dm : nullptr, payload_scalar, payload_threshold,
                                    tau_out ? dtau : nullptr, feasible_out ? dmask : nullptr, st));
-        if (tau_out) TCMP_CUDA(d2h_rows(tau_out, dtau, 7, n, off, len, esz, st));
-        if (feasible_out) TCMP_CUDA(d2h_rows(feasible_out, dmask, 1, n, off, len, 1, st));
+        if (tau_out) TCMP_CUDA_WS(ws, d2h_rows(tau_out, dtau, 7, n, off, len, esz, st));
+        if (feasible_out) TCMP_CUDA_WS(ws, d2h_rows(feasible_out, dmask, 1, n, off, len, 1, st));
     }
-    for (int s = 0; s < tcmp_workspace::kStages; ++s) TCMP_CUDA(cudaStreamSynchronize(ws->stream[s]));
+    TCMP_CUDA(ws_drain(ws));
     return TCMP_OK;
 }
 
@@ -378,6 +414,7 @@ int tcmp_edge_feasibility_host(tcmp_workspace *ws, int mode, int dtype, int64_t 
                                const void *qa, const void *qb, double payload_scalar, double payload_threshold,
                                int static_only, int32_t *first_fail_out) {
     if (!ws) return fail(TCMP_ERR_INVALID_ARG, "workspace is NULL");
+    DeviceScope scope(ws->device);
     if (int rc = check_common(mode, dtype, n_edges)) return rc;
     if (n_waypoints < 1) return fail(TCMP_ERR_INVALID_ARG, "n_waypoints must be >= 1");
     if (n_edges == 0) return TCMP_OK;
@@ -393,13 +430,13 @@ int tcmp_edge_feasibility_host(tcmp_workspace *ws, int mode, int dtype, int64_t 
         char *base = (char *)ws->dev[stage];
         char *da = base, *db = base + 7 * row;
         int32_t *dff = (int32_t *)(base + 14 * row);
-        TCMP_CUDA(h2d_rows(da, qa, 7, n_edges, off, len, esz, st));
-        TCMP_CUDA(h2d_rows(db, qb, 7, n_edges, off, len, esz, st));
-        TCMP_CUDA(launch_edge_feasibility(mode, dtype, len, n_waypoints, da, db, payload_scalar, payload_threshold,
+        TCMP_CUDA_WS(ws, h2d_rows(da, qa, 7, n_edges, off, len, esz, st));
+        TCMP_CUDA_WS(ws, h2d_rows(db, qb, 7, n_edges, off, len, esz, st));
+        TCMP_CUDA_WS(ws, launch_edge_feasibility(mode, dtype, len, n_waypoints, da, db, payload_scalar, payload_threshold,
                                           static_only, dff, st));
-        TCMP_CUDA(d2h_rows(first_fail_out, dff, 1, n_edges, off, len, 4, st));
+        TCMP_CUDA_WS(ws, d2h_rows(first_fail_out, dff, 1, n_edges, off, len, 4, st));
     }
-    for (int s = 0; s < tcmp_workspace::kStages; ++s) TCMP_CUDA(cudaStreamSynchronize(ws->stream[s]));
+    TCMP_CUDA(ws_drain(ws));
     return TCMP_OK;
 }
 
@@ -407,6 +444,7 @@ int tcmp_ik_batch_host(tcmp_workspace *ws, int64_t n, const double *rot9, const 
                        const double *free_vals, int n_free, int free_broadcast, double *sols_out, int32_t *count_out,
                        uint8_t *status_out) {
     if (!ws) return fail(TCMP_ERR_INVALID_ARG, "workspace is NULL");
+    DeviceScope scope(ws->device);
     if (n < 0 || n_free < 1) return fail(TCMP_ERR_INVALID_ARG, "bad n / n_free");
     if (n == 0) return TCMP_OK;
     if (!rot9 || !trans3 || !free_vals || !count_out) return fail(TCMP_ERR_INVALID_ARG, "NULL IK buffer");
@@ -426,21 +464,21 @@ int tcmp_ik_batch_host(tcmp_workspace *ws, int64_t n, const double *rot9, const 
         double *dsol = (double *)(base + (12 + n_free) * row);
         int32_t *dcnt = (int32_t *)((char *)dsol + solves * 56 * 8);
         uint8_t *dstat = (uint8_t *)((char *)dcnt + solves * 4);
-        TCMP_CUDA(h2d_rows(dr, rot9, 9, n, off, len, 8, st));
-        TCMP_CUDA(h2d_rows(dt, trans3, 3, n, off, len, 8, st));
+        TCMP_CUDA_WS(ws, h2d_rows(dr, rot9, 9, n, off, len, 8, st));
+        TCMP_CUDA_WS(ws, h2d_rows(dt, trans3, 3, n, off, len, 8, st));
         if (free_broadcast)
-            TCMP_CUDA(cudaMemcpyAsync(df, free_vals, (size_t)n_free * 8, cudaMemcpyHostToDevice, st));
+            TCMP_CUDA_WS(ws, cudaMemcpyAsync(df, free_vals, (size_t)n_free * 8, cudaMemcpyHostToDevice, st));
         else
-            TCMP_CUDA(h2d_rows(df, free_vals, n_free, n, off, len, 8, st));
-        TCMP_CUDA(launch_ik_batch(len, dr, dt, df, n_free, free_broadcast, sols_out ? dsol : nullptr, dcnt,
+            TCMP_CUDA_WS(ws, h2d_rows(df, free_vals, n_free, n, off, len, 8, st));
+        TCMP_CUDA_WS(ws, launch_ik_batch(len, dr, dt, df, n_free, free_broadcast, sols_out ? dsol : nullptr, dcnt,
                                   status_out ? dstat : nullptr, st));
         const size_t s0 = (size_t)off * n_free, sl = (size_t)len * n_free;
         if (sols_out)
-            TCMP_CUDA(cudaMemcpyAsync(sols_out + s0 * 56, dsol, sl * 56 * 8, cudaMemcpyDeviceToHost, st));
-        TCMP_CUDA(cudaMemcpyAsync(count_out + s0, dcnt, sl * 4, cudaMemcpyDeviceToHost, st));
-        if (status_out) TCMP_CUDA(cudaMemcpyAsync(status_out + s0, dstat, sl, cudaMemcpyDeviceToHost, st));
+            TCMP_CUDA_WS(ws, cudaMemcpyAsync(sols_out + s0 * 56, dsol, sl * 56 * 8, cudaMemcpyDeviceToHost, st));
+        TCMP_CUDA_WS(ws, cudaMemcpyAsync(count_out + s0, dcnt, sl * 4, cudaMemcpyDeviceToHost, st));
+        if (status_out) TCMP_CUDA_WS(ws, cudaMemcpyAsync(status_out + s0, dstat, sl, cudaMemcpyDeviceToHost, st));
     }
-    for (int s = 0; s < tcmp_workspace::kStages; ++s) TCMP_CUDA(cudaStreamSynchronize(ws->stream[s]));
+    TCMP_CUDA(ws_drain(ws));
     return TCMP_OK;
 }
 
@@ -458,23 +496,23 @@ int tcmp_fp64_peak(int iters, double *flops_out, void *stream) {
     if (iters < 1 || !flops_out) return fail(TCMP_ERR_INVALID_ARG, "bad fp64 peak args");
     cudaStream_t st = (cudaStream_t)stream;
     double *sink = nullptr;
-    TCMP_CUDA(cudaMalloc(&sink, 8));
-    cudaEvent_t e0, e1;
-    TCMP_CUDA(cudaEventCreate(&e0));
-    TCMP_CUDA(cudaEventCreate(&e1));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     int grid = 0, block = 0;
-    TCMP_CUDA(launch_fp64_peak(iters / 8 + 1, sink, &grid, &block, st));  // warm-up
-    TCMP_CUDA(cudaEventRecord(e0, st));
-    TCMP_CUDA(launch_fp64_peak(iters, sink, &grid, &block, st));
-    TCMP_CUDA(cudaEventRecord(e1, st));
-    TCMP_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
-    TCMP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    const double flops = 2.0 * 8 * 16 * (double)iters * (double)grid * block;
-    *flops_out = flops / (ms * 1e-3);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(sink);
+    cudaError_t e = cudaMalloc(&sink, 8);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = launch_fp64_peak(iters / 8 + 1, sink, &grid, &block, st);  // warm-up
+    if (e == cudaSuccess) e = cudaEventRecord(e0, st);
+    if (e == cudaSuccess) e = launch_fp64_peak(iters, sink, &grid, &block, st);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, st);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (sink) cudaFree(sink);
+    if (e != cudaSuccess) return cuda_fail(e, "tcmp_fp64_peak");
+    *flops_out = 2.0 * 8 * 16 * (double)iters * (double)grid * block / (ms * 1e-3);
     return TCMP_OK;
 }
 
