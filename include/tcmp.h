@@ -75,6 +75,34 @@ int tcmp_rne_batch(int mode, int dtype, int64_t n, const void *q, const void *qd
                    void *tau_out, uint8_t *feasible_out, void *stream);
 
 /*
+ * The inertial parameters and limits the torque test uses, for callers whose arm is not the stock one (another
+ * hand, recalibrated links, tighter limits).  The reference keeps these in module-level lists -- ms, cs,
+ * inertia_matrices (rne.py:102,119,138) -- plus the literals 0.14 + 0.025 (rne.py:182,186) and get_max_force
+ * (utils.py:1558); SURVEY.md 8b sketches a process-global `tcmp_set_model`.  Here the record is an ARGUMENT of
+ * the call instead, so the library keeps no mutable state and stays re-entrant.  The modified-DH geometry
+ * (rne.py:47-54) is not part of it: IK, FK and the collision model are built on the same geometry.
+ * All doubles, no padding (99 doubles): bindings may pass a flat float64[99].
+ */
+typedef struct tcmp_model {
+    double mass[9];         /* panda_link1..7, panda_link8, panda_hand                      rne.py:125-136 */
+    double com[9][3];       /* centre of mass in the body frame (link8 / hand: flange frame) rne.py:106-117 */
+    double inertia[9][6];   /* ixx ixy ixz iyy iyz izz about the centre of mass              rne.py:65-75   */
+    double payload_radius;  /* payload inertia = diag(m r^2, m r^2, 0), r = 0.165            rne.py:182-187 */
+    double tool_z;          /* grasp-target height above the flange, 0.105 (dyn)   panda_mod.urdf:87-91     */
+    double torque_limit[7]; /* 87 87 87 87 12 12 12; joint 7 is never tested       panda_primitives.py:182  */
+} tcmp_model;
+/* Fills *out with the compiled-in Panda (what every other entry point uses). */
+int tcmp_model_default(tcmp_model *out);
+/*
+ * tcmp_rne_batch with a caller-supplied inertial set (host pointer, read during the call; NULL = compiled-in
+ * Panda, then identical to tcmp_rne_batch).  The record is folded (link8 + hand onto link 7) and regrouped into
+ * base parameters on the host, then handed to the kernel by value.  Masses must be finite and >= 0, limits > 0.
+ */
+int tcmp_rne_batch_model(const tcmp_model *model, int mode, int dtype, int64_t n, const void *q, const void *qd,
+                         const void *qdd, const void *payload_mass, double payload_scalar,
+                         double payload_threshold, void *tau_out, uint8_t *feasible_out, void *stream);
+
+/*
  * Multi-GPU form of tcmp_rne_batch: the feasibility byte of state i is stored into dest_masks[d][dest_offset + i]
  * for every d < n_dest -- the gathered mask buffers of all ranks (this rank's own and its peers', mapped with
  * tcmp_peer_open over NVLink/NVSwitch).  This is the "NCCL all-gather of the masks" of BASELINE.json's

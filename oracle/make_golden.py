@@ -93,6 +93,53 @@ def gen_states(n=3000, seed=2):
     print("states_cfg2: rne feasible %.3f nov feasible %.3f" % (ok_rne.mean(), ok_nov.mean()))
 
 
+def custom_model(seed=21):
+    """A deliberately different inertial set: every mass / COM / inertia perturbed, a massive link8 with an off-axis
+    COM, a heavier hand with the real gripper's COM height, another payload lever and tighter limits."""
+    rng = np.random.default_rng(seed)
+    m = oracle.default_model()
+    f = oracle.model_fields(m)
+    f["mass"][:7] *= rng.uniform(0.7, 1.3, size=7)
+    f["mass"][7] = 0.2
+    f["mass"][8] = 1.1
+    f["com"][:7] += rng.normal(0, 0.01, size=(7, 3))
+    f["com"][7] = [0.01, -0.02, 0.03]
+    f["com"][8] = [0.005, 0.01, 0.06]
+    for k in range(9):
+        A = rng.normal(0, 1, size=(3, 3))
+        P = 0.002 * (A @ A.T)   # symmetric positive semi-definite perturbation
+        ixx, ixy, ixz, iyy, iyz, izz = f["inertia"][k]
+        I = np.array([[ixx, ixy, ixz], [ixy, iyy, iyz], [ixz, iyz, izz]]) + P
+        f["inertia"][k] = [I[0, 0], I[0, 1], I[0, 2], I[1, 1], I[1, 2], I[2, 2]]
+    f["payload_radius"][0] = 0.21
+    f["tool_z"][0] = 0.13
+    f["torque_limit"][:] = [80, 70, 60, 50, 11, 9, 12]
+    return m
+
+
+def gen_model(n=400, seed=22):
+    """Pins the model-parametrised form of the oracle: rne.rne executed with the module's inertial lists overwritten."""
+    model = custom_model()
+    f = oracle.model_fields(model)
+    q, qd, qdd, mass = sample_states(n, seed)
+    tau = np.zeros((7, n))
+    tau_static = np.zeros((7, n))
+    z = np.zeros(7)
+    with H.ref_inertial_override(f):
+        for i in range(n):
+            mp = mass[i] if mass[i] > 0.01 else 0.0
+            tau[:, i] = H.ref_rne_payload_radius(q[:, i], qd[:, i], qdd[:, i], mp, f["payload_radius"][0])
+            tau_static[:, i] = H.ref_rne_payload_radius(q[:, i], z, z, mp, f["payload_radius"][0])
+    # the tables are back: the stock KAT must reproduce
+    assert np.allclose(H.ref_rne(H.Q_HOME, z, z, 0.0), oracle.rne(H.Q_HOME, z, z, 0.0), atol=1e-12)
+    lim = f["torque_limit"][:6, None]
+    np.savez(os.path.join(OUT, "model_override.npz"), seed=seed, model=model, q=q, qd=qd, qdd=qdd, mass=mass,
+             tau_rne=tau, feasible_rne=(np.abs(tau[:6]) < lim).all(axis=0).astype(np.uint8),
+             tau_nov=tau_static, feasible_nov=(np.abs(tau_static[:6]) < lim).all(axis=0).astype(np.uint8))
+    t, ok = oracle.torque_test_batch("rne", q, qd, qdd, mass, model=model)
+    print("model_override: oracle vs reference %.2e N.m, feasible %.3f" % (np.abs(t - tau).max(), ok.mean()))
+
+
 def gen_minjerk(seed=11):
     rng = np.random.default_rng(seed)
     out = {}
@@ -175,7 +222,7 @@ def gen_ik(n=1500, n_free=4, seed=3):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     oracle.build()
-    which = sys.argv[1:] or ["kats", "states", "minjerk", "edges", "traj", "ik"]
+    which = sys.argv[1:] or ["kats", "states", "model", "minjerk", "edges", "traj", "ik"]
     for w in which:
-        {"kats": gen_kats, "states": gen_states, "minjerk": gen_minjerk, "edges": gen_edges,
+        {"kats": gen_kats, "states": gen_states, "model": gen_model, "minjerk": gen_minjerk, "edges": gen_edges,
          "traj": gen_traj, "ik": gen_ik}[w]()

@@ -72,6 +72,47 @@ def ref_torque_test(mode, q, qd=None, qdd=None, payload_mass=0.0):
     return ok, tau
 
 
+class ref_inertial_override:
+    """Context manager: overwrite the reference's module-level inertial tables IN PLACE (rne.py:102 inertia_matrices,
+    :119 cs, :138 ms are plain lists that rne() re-reads on every call, :212-216) with a flat model record
+    (oracle.model_fields layout), and restore them on exit.  No reference code is changed: rne() itself runs as is."""
+
+    def __init__(self, fields):
+        self.f = fields
+
+    def __enter__(self):
+        R, _ = _import()
+        R.remove_payload()
+        self.saved = (list(R.ms), [np.array(c, dtype=float) for c in R.cs], [np.array(i) for i in R.inertia_matrices])
+        for k in range(9):
+            R.ms[k] = float(self.f["mass"][k])
+            R.cs[k] = np.array(self.f["com"][k], dtype=float)
+            ixx, ixy, ixz, iyy, iyz, izz = (float(v) for v in self.f["inertia"][k])
+            R.inertia_matrices[k] = np.array([[ixx, ixy, ixz], [ixy, iyy, iyz], [ixz, iyz, izz]])  # rne.py:82
+        return self
+
+    def __exit__(self, *exc):
+        R, _ = _import()
+        R.remove_payload()
+        R.ms[:], R.cs[:], R.inertia_matrices[:] = self.saved
+        return False
+
+
+def ref_rne_payload_radius(q, qd, qdd, payload_mass, radius):
+    """rne.rne after the body of add_payload (rne.py:181-188) run with another lever than hand_width + 0.025:
+    the same four calls on the reference's own helpers, with new_inertia([0, 0, radius], m)."""
+    R, _ = _import()
+    R.remove_payload()
+    if payload_mass > 0:
+        R.set_has_payload(True)
+        R.add_mass_to_ms_global(float(payload_mass))
+        R.add_inertia_matrix(R.new_inertia([0, 0, float(radius)], float(payload_mass)))
+    try:
+        return np.asarray(R.rne(list(map(float, q)), list(map(float, qd)), list(map(float, qdd))), dtype=np.float64)
+    finally:
+        R.remove_payload()
+
+
 def ref_minjerk(points, num_intervals):
     """min_jerk_v2.minjerk_coefficients + minjerk_trajectory exactly as get_dynamics_fn_v5 calls them
     (panda_primitives.py:301,310).  Returns (coeffs [k][N][7], x, v, a each [samples][k])."""

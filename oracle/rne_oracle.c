@@ -37,31 +37,42 @@ static const double DH_D[8] = {0.333, 0, 0.316, 0, 0.384, 0, 0.0, 0.107};
 #define PI_ 3.141592653589793 /* np.pi */
 static const double DH_ALPHA[8] = {0, -PI_ / 2, PI_ / 2, PI_ / 2, -PI_ / 2, PI_ / 2, PI_ / 2, 0};
 
-/* rne.py:65-75 -- link inertias about the COM (ixx ixy ixz iyy iyz izz). */
-static const double LINK_I[9][6] = {
-    {7.0337e-01, -1.3900e-04, 6.7720e-03, 7.0661e-01, 1.9169e-02, 9.1170e-03},
-    {7.9620e-03, -3.9250e-03, 1.0254e-02, 2.8110e-02, 7.0400e-04, 2.5995e-02},
-    {3.7242e-02, -4.7610e-03, -1.1396e-02, 3.6155e-02, -1.2805e-02, 1.0830e-02},
-    {2.5853e-02, 7.7960e-03, -1.3320e-03, 1.9552e-02, 8.6410e-03, 2.8323e-02},
-    {3.5549e-02, -2.1170e-03, -4.0370e-03, 2.9474e-02, 2.2900e-04, 8.6270e-03},
-    {1.9640e-03, 1.0900e-04, -1.1580e-03, 4.3540e-03, 3.4100e-04, 5.4330e-03},
-    {1.2516e-02, -4.2800e-04, -1.1960e-03, 1.0027e-02, -7.4100e-04, 4.8150e-03},
-    {0.001, 0.0, 0.0, 0.001, 0.0, 0.001},
-    {0.1, 0.0, 0.0, 0.1, 0.0, 0.1},
-};
-/* rne.py:106-117 -- COMs; entry 9 (payload) stays (0,0,0): add_payload ignores r (rne.py:181-188). */
-static const double LINK_C[NLINK][3] = {
-    {3.875e-03, 2.081e-03, -0.1750},      {-3.141e-03, -2.872e-02, 3.495e-03},
-    {2.7518e-02, 3.9252e-02, -6.6502e-02}, {-5.317e-02, 1.04419e-01, 2.7454e-02},
-    {-1.1953e-02, 4.1065e-02, -3.8437e-02}, {6.0149e-02, -1.4117e-02, -1.0517e-02},
-    {1.0517e-02, -4.252e-03, 6.1597e-02},  {0, 0, 0}, {0, 0, 0}, {0, 0, 0},
-};
-/* rne.py:125-136 */
-static const double LINK_M[9] = {4.970684, 0.646926, 3.228604, 3.587895, 1.225946,
-                                 1.666555, 7.35522e-01, 0.0, 0.68};
+/*
+ * The inertial tables as one record, so the same restatement can be run with OTHER inertial parameters (a
+ * different hand, a recalibrated link): the reference keeps them in the module-level lists ms / cs /
+ * inertia_matrices (rne.py:102,119,138), which oracle/make_golden.py overwrites in place to pin this form.  Field
+ * order and sizes are those of `tcmp_model` (include/tcmp.h); the DH geometry is not part of it.
+ */
+typedef struct oracle_model {
+    double mass[9];         /* rne.py:125-136: panda_link1..7, panda_link8, panda_hand */
+    double com[9][3];       /* rne.py:106-117; the payload link's COM stays (0,0,0): add_payload ignores r (:181-188) */
+    double inertia[9][6];   /* rne.py:65-75: ixx ixy ixz iyy iyz izz about the COM */
+    double payload_radius;  /* rne.py:182,186: hand_width + 0.025 */
+    double tool_z;          /* panda_mod.urdf:87-91: grasp target past the flange (dyn mode) */
+    double torque_limit[7]; /* panda_primitives.py:162-166 + utils.py:1558 + panda_mod.urdf:127..283 (effort) */
+} oracle_model;
 
-/* panda_primitives.py:162-166 + utils.py:1558 + panda_mod.urdf:127..283 (effort limits). */
-static const double TAU_LIMIT[7] = {87, 87, 87, 87, 12, 12, 12};
+static const oracle_model PANDA = {
+    {4.970684, 0.646926, 3.228604, 3.587895, 1.225946, 1.666555, 7.35522e-01, 0.0, 0.68},
+    {{3.875e-03, 2.081e-03, -0.1750},       {-3.141e-03, -2.872e-02, 3.495e-03},
+     {2.7518e-02, 3.9252e-02, -6.6502e-02}, {-5.317e-02, 1.04419e-01, 2.7454e-02},
+     {-1.1953e-02, 4.1065e-02, -3.8437e-02}, {6.0149e-02, -1.4117e-02, -1.0517e-02},
+     {1.0517e-02, -4.252e-03, 6.1597e-02},  {0, 0, 0}, {0, 0, 0}},
+    {{7.0337e-01, -1.3900e-04, 6.7720e-03, 7.0661e-01, 1.9169e-02, 9.1170e-03},
+     {7.9620e-03, -3.9250e-03, 1.0254e-02, 2.8110e-02, 7.0400e-04, 2.5995e-02},
+     {3.7242e-02, -4.7610e-03, -1.1396e-02, 3.6155e-02, -1.2805e-02, 1.0830e-02},
+     {2.5853e-02, 7.7960e-03, -1.3320e-03, 1.9552e-02, 8.6410e-03, 2.8323e-02},
+     {3.5549e-02, -2.1170e-03, -4.0370e-03, 2.9474e-02, 2.2900e-04, 8.6270e-03},
+     {1.9640e-03, 1.0900e-04, -1.1580e-03, 4.3540e-03, 3.4100e-04, 5.4330e-03},
+     {1.2516e-02, -4.2800e-04, -1.1960e-03, 1.0027e-02, -7.4100e-04, 4.8150e-03},
+     {0.001, 0.0, 0.0, 0.001, 0.0, 0.001},
+     {0.1, 0.0, 0.0, 0.1, 0.0, 0.1}},
+    0.14 + 0.025,
+    0.105,
+    {87, 87, 87, 87, 12, 12, 12},
+};
+
+void oracle_model_default(oracle_model *m) { *m = PANDA; }
 
 /* ---- small dense helpers (row-major) ------------------------------------ */
 static void skew(const double v[3], double S[3][3]) { /* rne.py:4-7 */
@@ -180,8 +191,8 @@ static void spatial_inertia(double m, const double c[3], const double I6[6], dou
  * explicit argument: has_payload / payload_mass are what add_payload(r, m)
  * (rne.py:181-188) would have left in the globals.
  */
-void oracle_rne(const double q7[7], const double qd7[7], const double qdd7[7],
-                int has_payload, double payload_mass, double tau_out[7]) {
+static void rne_with(const oracle_model *mdl, const double q7[7], const double qd7[7], const double qdd7[7],
+                     int has_payload, double payload_mass, double tau_out[7]) {
     double q[NLINK] = {0}, qd[NLINK] = {0}, qdd[NLINK] = {0}; /* rne.py:206-208 */
     for (int i = 0; i < 7; i++) {
         q[i] = q7[i];
@@ -217,11 +228,13 @@ void oracle_rne(const double q7[7], const double qd7[7], const double qdd7[7],
 
         /* rne.py:240-241  f = I a + crf(v) @ I @ v, crf = -crm^T (rne.py:26-27) */
         double m, I6[6];
+        static const double payload_com[3] = {0, 0, 0}; /* add_payload ignores r: rne.py:181-188 */
+        const double *com = k < 9 ? mdl->com[k] : payload_com;
         if (k < 9) {
-            m = LINK_M[k];
-            memcpy(I6, LINK_I[k], sizeof(I6));
+            m = mdl->mass[k];
+            memcpy(I6, mdl->inertia[k], sizeof(I6));
         } else { /* payload link: rne.py:85-100 new_inertia([0,0,0.14+0.025], m) */
-            const double r[3] = {0, 0, 0.14 + 0.025};
+            const double r[3] = {0, 0, mdl->payload_radius};
             m = payload_mass;
             I6[0] = m * (r[1] * r[1] + r[2] * r[2]);
             I6[1] = -m * (r[0] * r[1]);
@@ -231,7 +244,7 @@ void oracle_rne(const double q7[7], const double qd7[7], const double qdd7[7],
             I6[5] = m * (r[0] * r[0] + r[1] * r[1]);
         }
         double S[6][6], M[6][6], F[6][6], FS[6][6], t1[6], t2[6];
-        spatial_inertia(m, LINK_C[k], I6, S);
+        spatial_inertia(m, com, I6, S);
         crm(v[k], M);
         for (int r = 0; r < 6; r++)
             for (int c2 = 0; c2 < 6; c2++) F[r][c2] = -M[c2][r];
@@ -259,13 +272,19 @@ void oracle_rne(const double q7[7], const double qd7[7], const double qdd7[7],
     for (int i = 0; i < 7; i++) tau_out[i] = tau[i]; /* rne.py:253 */
 }
 
+void oracle_rne(const double q7[7], const double qd7[7], const double qdd7[7],
+                int has_payload, double payload_mass, double tau_out[7]) {
+    rne_with(&PANDA, q7, qd7, qdd7, has_payload, payload_mass, tau_out);
+}
+
 /* panda_primitives.py:182-188: infeasible iff any |tau_i| >= limit_i for i in 0..5
  * (range(len(max_limits)-1): joint 7 is never tested; EPS = 1, :165). */
-int oracle_within_limits(const double tau[7]) {
+static int within_limits_of(const oracle_model *mdl, const double tau[7]) {
     for (int i = 0; i < 6; i++)
-        if (fabs(tau[i]) >= TAU_LIMIT[i] * 1) return 0;
+        if (fabs(tau[i]) >= mdl->torque_limit[i] * 1) return 0;
     return 1;
 }
+int oracle_within_limits(const double tau[7]) { return within_limits_of(&PANDA, tau); }
 
 /* ---- forward kinematics of the DH chain (used by the defined `dyn` oracle) --- */
 static void mm4(const double A[4][4], const double B[4][4], double C[4][4]) {
@@ -299,10 +318,10 @@ static void dh_matrix(int k, double theta, double T[4][4]) {
  * J^T F with F = (0,0,m g) is  tau_i = m g * (z_i x (p_tool - p_i)).z.
  * The reference applies payload_mass unconditionally here (no 0.01 threshold, :71-76).
  */
-void oracle_dyn(const double q[7], const double qd[7], const double qdd[7],
-                double payload_mass, double tau_out[7]) {
+static void dyn_with(const oracle_model *mdl, const double q[7], const double qd[7], const double qdd[7],
+                     double payload_mass, double tau_out[7]) {
     double tau[7];
-    oracle_rne(q, qd, qdd, 0, 0.0, tau);
+    rne_with(mdl, q, qd, qdd, 0, 0.0, tau);
     double T[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
     double z[7][3], p[7][3];
     for (int k = 0; k < 8; k++) {
@@ -318,13 +337,17 @@ void oracle_dyn(const double q[7], const double qd[7], const double qdd[7],
     }
     /* tool origin: the hand's Rz(-pi/4) does not move a point on its z axis */
     double pt[3];
-    for (int r = 0; r < 3; r++) pt[r] = T[r][3] + T[r][2] * 0.105;
+    for (int r = 0; r < 3; r++) pt[r] = T[r][3] + T[r][2] * mdl->tool_z;
     const double force = payload_mass * 9.81; /* panda_primitives.py:101 */
     for (int i = 0; i < 7; i++) {
         double dx = pt[0] - p[i][0], dy = pt[1] - p[i][1];
         double jz = z[i][0] * dy - z[i][1] * dx; /* (z_i x d).z */
         tau_out[i] = jz * force + tau[i];
     }
+}
+void oracle_dyn(const double q[7], const double qd[7], const double qdd[7],
+                double payload_mass, double tau_out[7]) {
+    dyn_with(&PANDA, q, qd, qdd, payload_mass, tau_out);
 }
 
 /*
@@ -333,8 +356,9 @@ void oracle_dyn(const double q[7], const double qd[7], const double qdd[7],
  * payload_threshold is 0.01 for the reference's closures (:139,:178); the raw
  * rne.add_payload() rule is `m > 0` (rne.py:184), i.e. threshold 0.
  */
-int oracle_torque_test(int mode, const double q[7], const double qd[7], const double qdd[7],
-                       double payload_mass, double payload_threshold, double tau_out[7]) {
+static int torque_test_with(const oracle_model *mdl, int mode, const double q[7], const double qd[7],
+                            const double qdd[7], double payload_mass, double payload_threshold,
+                            double tau_out[7]) {
     static const double Z[7] = {0, 0, 0, 0, 0, 0, 0};
     double tau[7] = {0};
     if (mode == 3) {
@@ -344,21 +368,26 @@ int oracle_torque_test(int mode, const double q[7], const double qd[7], const do
     const double *v = (mode == 1 || !qd) ? Z : qd;
     const double *a = (mode == 1 || !qdd) ? Z : qdd;
     if (mode == 2) {
-        oracle_dyn(q, v, a, payload_mass, tau);
+        dyn_with(mdl, q, v, a, payload_mass, tau);
     } else {
         int has = payload_mass > payload_threshold;
-        oracle_rne(q, v, a, has, has ? payload_mass : 0.0, tau);
+        rne_with(mdl, q, v, a, has, has ? payload_mass : 0.0, tau);
     }
     if (tau_out) memcpy(tau_out, tau, sizeof(tau));
-    return oracle_within_limits(tau);
+    return within_limits_of(mdl, tau);
+}
+int oracle_torque_test(int mode, const double q[7], const double qd[7], const double qdd[7],
+                       double payload_mass, double payload_threshold, double tau_out[7]) {
+    return torque_test_with(&PANDA, mode, q, qd, qdd, payload_mass, payload_threshold, tau_out);
 }
 
 /* Batched, SoA [7][n] like the C-ABI; OpenMP over states when built with -fopenmp.
  * payload_mass may be NULL (payload_scalar is used for every state). */
-void oracle_torque_test_batch(int mode, int64_t n, const double *q, const double *qd,
-                              const double *qdd, const double *payload_mass,
-                              double payload_scalar, double payload_threshold,
-                              double *tau_out, uint8_t *feasible_out, int nthreads) {
+void oracle_torque_test_batch_model(const oracle_model *mdl, int mode, int64_t n, const double *q,
+                                    const double *qd, const double *qdd, const double *payload_mass,
+                                    double payload_scalar, double payload_threshold, double *tau_out,
+                                    uint8_t *feasible_out, int nthreads) {
+    if (!mdl) mdl = &PANDA;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #pragma omp parallel for schedule(static)
@@ -371,11 +400,18 @@ void oracle_torque_test_batch(int mode, int64_t n, const double *q, const double
             as[j] = qdd ? qdd[j * n + s] : 0.0;
         }
         double m = payload_mass ? payload_mass[s] : payload_scalar;
-        int ok = oracle_torque_test(mode, qs, vs, as, m, payload_threshold, tau);
+        int ok = torque_test_with(mdl, mode, qs, vs, as, m, payload_threshold, tau);
         if (tau_out)
             for (int j = 0; j < 7; j++) tau_out[j * n + s] = tau[j];
         if (feasible_out) feasible_out[s] = (uint8_t)ok;
     }
+}
+void oracle_torque_test_batch(int mode, int64_t n, const double *q, const double *qd,
+                              const double *qdd, const double *payload_mass,
+                              double payload_scalar, double payload_threshold,
+                              double *tau_out, uint8_t *feasible_out, int nthreads) {
+    oracle_torque_test_batch_model(&PANDA, mode, n, q, qd, qdd, payload_mass, payload_scalar,
+                                   payload_threshold, tau_out, feasible_out, nthreads);
 }
 
 /* ---- min-jerk (min_jerk_v2.py) ------------------------------------------- */

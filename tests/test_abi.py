@@ -4,6 +4,8 @@ import os
 import re
 
 import numpy as np
+
+import oracle
 import pytest
 
 from conftest import ROOT
@@ -46,6 +48,31 @@ def test_argument_validation_without_gpu():
     assert lib.tcmp_edge_feasibility(0, 0, 4, 0, None, None, 0.0, 0.01, 0, None, None) == -1
     assert lib.tcmp_ik_batch(4, None, None, None, 1, 0, None, None, None, None) == -1
     assert lib.tcmp_ik_batch(0, None, None, None, 1, 0, None, None, None, None) == 0
+
+
+def test_model_record_without_gpu():
+    """tcmp_model_default fills the reference's tables (no CUDA call), and a malformed record is rejected before any."""
+    from torque_constrained_motion_planning_b200 import engine
+    m = engine.InertialModel.default()
+    assert np.array_equal(m.record, oracle.default_model())
+    assert m.mass[8] == 0.68 and m.payload_radius == 0.14 + 0.025 and m.tool_z == 0.105
+    lib = _lib.load()
+    bad = engine.InertialModel.default()
+    bad.mass[3] = -1.0
+    assert lib.tcmp_rne_batch_model(bad.record.ctypes.data, 0, 0, 0, None, None, None, None, 0.0, 0.01, None, None,
+                                    None) == -1
+    assert b"mass" in lib.tcmp_last_error()
+    bad = engine.InertialModel.default()
+    bad.torque_limit[2] = 0.0
+    assert lib.tcmp_rne_batch_model(bad.record.ctypes.data, 0, 0, 0, None, None, None, None, 0.0, 0.01, None, None,
+                                    None) == -1
+    bad.torque_limit[2] = float("nan")
+    assert lib.tcmp_rne_batch_model(bad.record.ctypes.data, 0, 0, 0, None, None, None, None, 0.0, 0.01, None, None,
+                                    None) == -1
+    ok = engine.InertialModel.default()
+    assert lib.tcmp_rne_batch_model(ok.record.ctypes.data, 0, 0, 0, None, None, None, None, 0.0, 0.01, None, None,
+                                    None) == 0
+    assert lib.tcmp_model_default(None) == -1
 
 
 def test_limits_table():

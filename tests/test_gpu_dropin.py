@@ -39,6 +39,26 @@ def test_rne_module_surface_and_payload_state():
     assert np.abs(tau - tau_o).max() < 1e-9
 
 
+def test_rne_module_with_another_inertial_set():
+    """What editing rne.py's ms / cs / inertia_matrices does in the reference: set_inertial_model here."""
+    from torque_constrained_motion_planning_b200 import engine, rne as R
+    g = load_golden("model_override.npz")
+    assert R.get_ms_global()[:9] == engine.InertialModel.default().mass.tolist() and len(R.get_ms_global()) == 10
+    R.set_inertial_model(engine.InertialModel(g["model"]))
+    try:
+        for i in range(0, 40):
+            m = float(g["mass"][i])
+            R.add_payload([0, 0, 0.03], m)
+            tau = R.rne(g["q"][:, i], g["qd"][:, i], g["qdd"][:, i])
+            assert np.abs(tau - g["tau_rne"][:, i]).max() < 1e-9
+            assert R.get_ms_global()[9] == m and R.get_ms_global()[8] == g["model"][8]
+            R.remove_payload()
+    finally:
+        R.set_inertial_model(None)
+    z = np.zeros(7)
+    assert np.abs(R.rne(Q_HOME, z, z) - oracle.rne(Q_HOME, z, z)).max() < 1e-9
+
+
 def test_ikfast_module_surface():
     from torque_constrained_motion_planning_b200 import ikfast_panda_arm as ik
     pos, rot = ik.get_fk(list(Q_HOME))

@@ -451,3 +451,49 @@ def test_edge_kernel_fp32_path(eng):
     # fp32 may move a first failure only where a torque sits within fp32 resolution of a limit
     assert (ff == ff_o).mean() > 0.995
     assert ((ff >= 0) & (ff <= 64)).all()
+
+
+@pytest.mark.parametrize("mode", ["rne", "nov", "dyn"])
+def test_model_override_vs_oracle(eng, mode):
+    """tcmp_rne_batch_model with another inertial set: 200k states against the model-parametrised oracle (itself
+    pinned to rne.py with overwritten tables, tests/golden/model_override.npz)."""
+    g = load_golden("model_override.npz")
+    model = eng.InertialModel(g["model"])
+    q, qd, qdd, mass = sample_states(200_000, seed=41)
+    tau, ok = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode=mode, model=model)
+    tau_o, ok_o = oracle.torque_test_batch(mode, q, qd, qdd, mass, model=g["model"])
+    assert np.abs(tau.cpu().numpy() - tau_o).max() < 1e-9
+    assert np.array_equal(ok.cpu().numpy(), ok_o)
+    # outputs are independently optional, host arrays are staged
+    _, ok_only = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode=mode, model=model, want_tau=False)
+    assert np.array_equal(ok_only.cpu().numpy(), ok_o)
+    tau_h, ok_h = eng.torque_test_batch(q[:, :999], qd[:, :999], qdd[:, :999], mass[:999], mode=mode, model=model)
+    assert np.abs(tau_h - tau_o[:, :999]).max() < 1e-9 and np.array_equal(ok_h, ok_o[:999])
+
+
+def test_model_override_vs_reference_golden(eng):
+    g = load_golden("model_override.npz")
+    model = eng.InertialModel(g["model"])
+    tau, ok = eng.torque_test_batch(dev(g["q"]), dev(g["qd"]), dev(g["qdd"]), dev(g["mass"]), model=model)
+    assert np.abs(tau.cpu().numpy() - g["tau_rne"]).max() < 1e-9 and np.array_equal(ok.cpu().numpy(), g["feasible_rne"])
+    tau, ok = eng.torque_test_batch(dev(g["q"]), None, None, dev(g["mass"]), mode="nov", model=model)
+    assert np.abs(tau.cpu().numpy() - g["tau_nov"]).max() < 1e-9 and np.array_equal(ok.cpu().numpy(), g["feasible_nov"])
+
+
+def test_default_model_record_equals_compiled_in_kernels(eng):
+    """The run-time folded default record and the compile-time constants are the same robot; fp32 too."""
+    q, qd, qdd, mass = sample_states(100_000, seed=42)
+    d = eng.InertialModel.default()
+    for mode in ("rne", "nov", "dyn"):
+        a, oa = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode=mode)
+        b, ob = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode=mode, model=d)
+        assert (a - b).abs().max().item() < 1e-11 and bool((oa == ob).all())
+    a, _ = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), dtype="f32")
+    b, _ = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), dtype="f32", model=d)
+    assert (a - b).abs().max().item() < 2e-3     # both fp32: rounding of two evaluation orders
+    _, ok = eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), mode="base", model=d)
+    assert bool(ok.all())
+    bad = eng.InertialModel.default()
+    bad.mass[0] = float("inf")
+    with pytest.raises(eng.TcmpError, match="mass"):
+        eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), model=bad)

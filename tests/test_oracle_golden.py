@@ -62,6 +62,22 @@ def test_states_cfg2(mode):
     assert 0.05 < 1.0 - ok.mean() < 0.5 or mode == "nov"  # the set exercises both outcomes
 
 
+def test_model_override_vs_reference():
+    """The model-parametrised oracle against rne.py run with its module-level inertial lists overwritten
+    (oracle/make_golden.py gen_model): every link perturbed, link8 massive with an off-axis COM, another payload
+    lever, tighter limits."""
+    g = load_golden("model_override.npz")
+    tau, ok = oracle.torque_test_batch("rne", g["q"], g["qd"], g["qdd"], g["mass"], model=g["model"])
+    assert np.abs(tau - g["tau_rne"]).max() < 1e-12 and (ok == g["feasible_rne"]).all()
+    tau, ok = oracle.torque_test_batch("nov", g["q"], None, None, g["mass"], model=g["model"])
+    assert np.abs(tau - g["tau_nov"]).max() < 1e-12 and (ok == g["feasible_nov"]).all()
+    # and it is a different robot: the stock tables give other torques on the same states
+    tau0, _ = oracle.torque_test_batch("rne", g["q"], g["qd"], g["qdd"], g["mass"])
+    assert np.abs(tau0 - g["tau_rne"]).max() > 1.0
+    assert np.array_equal(oracle.torque_test_batch("rne", g["q"], g["qd"], g["qdd"], g["mass"],
+                                                   model=oracle.default_model())[0], tau0)
+
+
 def test_base_mode_is_constant_true():
     g = load_golden("states_cfg2.npz")
     tau, ok = oracle.torque_test_batch("base", g["q"], g["qd"], g["qdd"], g["mass"])

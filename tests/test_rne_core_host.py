@@ -1,0 +1,108 @@
+"""CPU: the product's RNE recursion (csrc/panda_model.cuh -- the same source the CUDA kernels instantiate: the
+customised 3-vector Newton-Euler, the compile-time base-parameter regrouping, the joint sincos and the run-time
+model folding of tcmp_rne_batch_model) built for the host by tests/native/rne_host.cpp and compared with the
+oracle and with the golden vectors the reference produced.  A test harness only: libtcmp.so has no CPU path."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT, load_golden, sample_states
+
+NATIVE = os.path.join(ROOT, "tests", "native")
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+@pytest.fixture(scope="module")
+def host_rne():
+    so = os.path.join(NATIVE, "librne_host.so")
+    src = os.path.join(NATIVE, "rne_host.cpp")
+    core = os.path.join(ROOT, "torque_constrained_motion_planning_b200", "csrc", "panda_model.cuh")
+    hdr = os.path.join(ROOT, "include", "tcmp.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in (src, core, hdr)):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-o", so, src])
+    L = ctypes.CDLL(so)
+
+    def fn(mode, q, qd=None, qdd=None, mass=0.0, threshold=0.01, model=None):
+        arr = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        q, qd, qdd = arr(q), arr(qd), arr(qdd)
+        n = q.shape[1]
+        pm = None if np.ndim(mass) == 0 else arr(mass)
+        tau = np.empty((7, n))
+        ok = np.empty(n, np.uint8)
+        p = lambda a: None if a is None else a.ctypes.data_as(_dp)
+        mdl = arr(model)
+        L.host_rne_batch(p(mdl), oracle.MODES[mode], ctypes.c_int64(n), p(q), p(qd), p(qdd), p(pm),
+                         ctypes.c_double(0.0 if pm is not None else float(mass)), ctypes.c_double(threshold),
+                         p(tau), ok.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+        return tau, ok
+    return fn
+
+
+@pytest.mark.parametrize("mode", ["rne", "nov", "dyn"])
+def test_compiled_in_panda_matches_oracle(host_rne, mode):
+    q, qd, qdd, mass = sample_states(20000, seed=31)
+    tau, ok = host_rne(mode, q, qd, qdd, mass)
+    tau_o, ok_o = oracle.torque_test_batch(mode, q, qd, qdd, mass)
+    assert np.abs(tau - tau_o).max() < 1e-11
+    assert np.array_equal(ok, ok_o)
+
+
+def test_compiled_in_panda_matches_reference_golden(host_rne):
+    g = load_golden("states_cfg2.npz")
+    tau, ok = host_rne("rne", g["q"], g["qd"], g["qdd"], g["mass"])
+    assert np.abs(tau - g["tau_rne"]).max() < 1e-11 and np.array_equal(ok, g["feasible_rne"])
+    tau, ok = host_rne("nov", g["q"], None, None, g["mass"])
+    assert np.abs(tau - g["tau_nov"]).max() < 1e-11 and np.array_equal(ok, g["feasible_nov"])
+
+
+def test_static_call_without_velocities(host_rne):
+    q, _, _, mass = sample_states(2000, seed=32)
+    tau, ok = host_rne("rne", q, None, None, mass)
+    tau_o, ok_o = oracle.torque_test_batch("rne", q, None, None, mass)
+    assert np.abs(tau - tau_o).max() < 1e-11 and np.array_equal(ok, ok_o)
+
+
+def test_large_and_nonfinite_angles_follow_libm(host_rne):
+    """Angles beyond 1e5 rad (or non-finite) leave the joint fast sincos for libm's: still the oracle's result."""
+    q, qd, qdd, mass = sample_states(512, seed=33)
+    q[3, ::7] += 2e5
+    q[5, ::11] = 1e300
+    tau, ok = host_rne("rne", q, qd, qdd, mass)
+    tau_o, ok_o = oracle.torque_test_batch("rne", q, qd, qdd, mass)
+    assert np.abs(tau - tau_o).max() < 1e-9 and np.array_equal(ok, ok_o)
+    q[2, 0] = np.nan
+    tau, ok = host_rne("rne", q, qd, qdd, mass)
+    assert np.isnan(tau[:, 0]).any() and ok[0] == 1   # NaN never compares >= limit (panda_primitives.py:182-183)
+
+
+def test_default_record_is_the_compiled_in_panda(host_rne):
+    """Folding + regrouping the default record at run time reproduces the compile-time constants' torques."""
+    q, qd, qdd, mass = sample_states(5000, seed=34)
+    for mode in ("rne", "nov", "dyn"):
+        a, oa = host_rne(mode, q, qd, qdd, mass)
+        b, ob = host_rne(mode, q, qd, qdd, mass, model=oracle.default_model())
+        assert np.abs(a - b).max() < 1e-12 and np.array_equal(oa, ob)
+
+
+def test_model_override_matches_reference_golden(host_rne):
+    """rne.py executed with its inertial lists overwritten (oracle/make_golden.py gen_model): a massive link8 with an
+    off-axis COM, a heavier hand, perturbed links, another payload lever, tighter limits."""
+    g = load_golden("model_override.npz")
+    tau, ok = host_rne("rne", g["q"], g["qd"], g["qdd"], g["mass"], model=g["model"])
+    assert np.abs(tau - g["tau_rne"]).max() < 1e-11 and np.array_equal(ok, g["feasible_rne"])
+    tau, ok = host_rne("nov", g["q"], None, None, g["mass"], model=g["model"])
+    assert np.abs(tau - g["tau_nov"]).max() < 1e-11 and np.array_equal(ok, g["feasible_nov"])
+
+
+@pytest.mark.parametrize("mode", ["rne", "nov", "dyn"])
+def test_model_override_matches_oracle(host_rne, mode):
+    g = load_golden("model_override.npz")
+    q, qd, qdd, mass = sample_states(10000, seed=35)
+    tau, ok = host_rne(mode, q, qd, qdd, mass, model=g["model"])
+    tau_o, ok_o = oracle.torque_test_batch(mode, q, qd, qdd, mass, model=g["model"])
+    assert np.abs(tau - tau_o).max() < 1e-11 and np.array_equal(ok, ok_o)

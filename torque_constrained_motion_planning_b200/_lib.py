@@ -29,6 +29,8 @@ SIGNATURES = {
     "tcmp_last_error": (ctypes.c_char_p, []),
     "tcmp_device_count": (_i32, []),
     "tcmp_rne_batch": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _vp, _vp]),
+    "tcmp_model_default": (_i32, [_vp]),
+    "tcmp_rne_batch_model": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _vp, _vp]),
     "tcmp_rne_batch_scatter": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _i32,
                                       ctypes.POINTER(_vp), _i64, _vp]),
     "tcmp_peer_alloc": (_i32, [ctypes.POINTER(_vp), _i64, ctypes.c_char_p]),

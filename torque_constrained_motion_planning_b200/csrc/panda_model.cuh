@@ -23,8 +23,21 @@
 // config-2 distribution, budget 1e-9).  The reference leaves cos(+-pi/2) = 6.1e-17 unsnapped
 // (rne.py:39-42); that contributes < 1e-15 N.m and is dropped here.
 #pragma once
-#include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+#include <string.h>
+#include <type_traits>
+
+#include "../../include/tcmp.h"
+// The recursion is plain arithmetic, so the SAME source also builds for the host: tests/native/rne_host.cpp
+// compiles it with g++ and checks it against the oracle on a CPU-only box (a test harness -- libtcmp.so contains
+// only the device code, there is no CPU path in the product).
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define TCMP_FN __host__ __device__ __forceinline__
+#else
+#define TCMP_FN inline
+#endif
 
 namespace tcmp {
 
@@ -40,7 +53,8 @@ struct LinkConst {
 constexpr double kGravity = 9.81;             // rne.py:199
 constexpr double kFlangeZ = 0.107;            // DH row 7 d (rne.py:54): link7 -> link8 / hand / payload frames
 constexpr double kPayloadR = 0.14 + 0.025;    // rne.py:182,186: new_inertia([0,0,hand_width+0.025], m)
-constexpr double kToolZ = 0.107 + 0.105;      // panda_grasptarget origin in the link-7 frame (panda_mod.urdf:87-91)
+constexpr double kToolOffset = 0.105;         // panda_grasptarget above the flange (panda_mod.urdf:87-91)
+constexpr double kToolZ = kFlangeZ + kToolOffset;   // ... in the link-7 frame
 
 constexpr LinkConst make_link(int alpha, double a, double d, double m, double cx, double cy, double cz,
                               double ixx, double ixy, double ixz, double iyy, double iyz, double izz) {
@@ -61,34 +75,41 @@ constexpr LinkConst make_link(int alpha, double a, double d, double m, double cx
     return L;
 }
 
+// DH row j (rne.py:47-53): alpha code, a along x (Khalil's d_j), d along z (Khalil's r_j)
+constexpr int kAlpha[7] = {0, -1, +1, +1, -1, +1, +1};
+constexpr double kA[7] = {0, 0, 0, 0.0825, -0.0825, 0, 0.088};
+constexpr double kD[7] = {0.333, 0, 0.316, 0, 0.384, 0, 0};
+// The reference's inertial tables: panda_link1..7, panda_link8, panda_hand (also what tcmp_model_default returns).
+constexpr double kMass[9] = {4.970684, 0.646926, 3.228604, 3.587895, 1.225946,                     // rne.py:125-136
+                             1.666555, 7.35522e-01, 0.0, 0.68};
+constexpr double kCom[9][3] = {{3.875e-03, 2.081e-03, -0.1750},        {-3.141e-03, -2.872e-02, 3.495e-03},   // rne.py:106-117
+                               {2.7518e-02, 3.9252e-02, -6.6502e-02},  {-5.317e-02, 1.04419e-01, 2.7454e-02},
+                               {-1.1953e-02, 4.1065e-02, -3.8437e-02}, {6.0149e-02, -1.4117e-02, -1.0517e-02},
+                               {1.0517e-02, -4.252e-03, 6.1597e-02},   {0, 0, 0}, {0, 0, 0}};
+constexpr double kInertia[9][6] = {{7.0337e-01, -1.3900e-04, 6.7720e-03, 7.0661e-01, 1.9169e-02, 9.1170e-03},   // rne.py:65-75
+                                   {7.9620e-03, -3.9250e-03, 1.0254e-02, 2.8110e-02, 7.0400e-04, 2.5995e-02},
+                                   {3.7242e-02, -4.7610e-03, -1.1396e-02, 3.6155e-02, -1.2805e-02, 1.0830e-02},
+                                   {2.5853e-02, 7.7960e-03, -1.3320e-03, 1.9552e-02, 8.6410e-03, 2.8323e-02},
+                                   {3.5549e-02, -2.1170e-03, -4.0370e-03, 2.9474e-02, 2.2900e-04, 8.6270e-03},
+                                   {1.9640e-03, 1.0900e-04, -1.1580e-03, 4.3540e-03, 3.4100e-04, 5.4330e-03},
+                                   {1.2516e-02, -4.2800e-04, -1.1960e-03, 1.0027e-02, -7.4100e-04, 4.8150e-03},
+                                   {0.001, 0.0, 0.0, 0.001, 0.0, 0.001},
+                                   {0.1, 0.0, 0.0, 0.1, 0.0, 0.1}};
+
 // Link k = panda_link(k+1).  Link 6 additionally carries link8 (m = 0, I = 0.001*1) and the hand
 // (m = 0.68, c = 0, I = 0.1*1), both rigidly at (0,0,0.107) in its frame (rne.py:54,58-61).
 constexpr LinkConst raw_link_const(int k) {
-    switch (k) {
-        case 0: return make_link(0, 0.0, 0.333, 4.970684, 3.875e-03, 2.081e-03, -0.1750,
-                                 7.0337e-01, -1.3900e-04, 6.7720e-03, 7.0661e-01, 1.9169e-02, 9.1170e-03);
-        case 1: return make_link(-1, 0.0, 0.0, 0.646926, -3.141e-03, -2.872e-02, 3.495e-03,
-                                 7.9620e-03, -3.9250e-03, 1.0254e-02, 2.8110e-02, 7.0400e-04, 2.5995e-02);
-        case 2: return make_link(+1, 0.0, 0.316, 3.228604, 2.7518e-02, 3.9252e-02, -6.6502e-02,
-                                 3.7242e-02, -4.7610e-03, -1.1396e-02, 3.6155e-02, -1.2805e-02, 1.0830e-02);
-        case 3: return make_link(+1, 0.0825, 0.0, 3.587895, -5.317e-02, 1.04419e-01, 2.7454e-02,
-                                 2.5853e-02, 7.7960e-03, -1.3320e-03, 1.9552e-02, 8.6410e-03, 2.8323e-02);
-        case 4: return make_link(-1, -0.0825, 0.384, 1.225946, -1.1953e-02, 4.1065e-02, -3.8437e-02,
-                                 3.5549e-02, -2.1170e-03, -4.0370e-03, 2.9474e-02, 2.2900e-04, 8.6270e-03);
-        case 5: return make_link(+1, 0.0, 0.0, 1.666555, 6.0149e-02, -1.4117e-02, -1.0517e-02,
-                                 1.9640e-03, 1.0900e-04, -1.1580e-03, 4.3540e-03, 3.4100e-04, 5.4330e-03);
-        default: {
-            LinkConst L = make_link(+1, 0.088, 0.0, 7.35522e-01, 1.0517e-02, -4.252e-03, 6.1597e-02,
-                                    1.2516e-02, -4.2800e-04, -1.1960e-03, 1.0027e-02, -7.4100e-04, 4.8150e-03);
-            const double mh = 0.68, z = kFlangeZ;   // hand; link8 has zero mass
-            L.m += mh;
-            L.hz += mh * z;
-            L.jxx += 0.001 + 0.1 + mh * z * z;
-            L.jyy += 0.001 + 0.1 + mh * z * z;
-            L.jzz += 0.001 + 0.1;
-            return L;
-        }
+    LinkConst L = make_link(kAlpha[k], kA[k], kD[k], kMass[k], kCom[k][0], kCom[k][1], kCom[k][2], kInertia[k][0],
+                            kInertia[k][1], kInertia[k][2], kInertia[k][3], kInertia[k][4], kInertia[k][5]);
+    if (k == 6) {
+        const double mh = kMass[8], z = kFlangeZ;   // hand; link8 has zero mass, both have c = 0 and diagonal I
+        L.m += mh;
+        L.hz += mh * z;
+        L.jxx += kInertia[7][0] + kInertia[8][0] + mh * z * z;
+        L.jyy += kInertia[7][3] + kInertia[8][3] + mh * z * z;
+        L.jzz += kInertia[7][5] + kInertia[8][5];
     }
+    return L;
 }
 // ---- regrouped (base) inertial parameters ---------------------------------------------------
 // Joint torques of a serial chain depend on fewer parameters than 10 per link: for a revolute joint j the
@@ -101,12 +122,9 @@ constexpr LinkConst raw_link_const(int k) {
 struct Model {
     LinkConst L[7];
 };
-constexpr Model make_model() {
-    Model M{};
-    for (int k = 0; k < 7; ++k) M.L[k] = raw_link_const(k);
-    // DH row j: alpha code, d_j (Khalil) = a along x, r_j = d along z
-    constexpr double kA[7] = {0, 0, 0, 0.0825, -0.0825, 0, 0.088};
-    constexpr double kD[7] = {0.333, 0, 0.316, 0, 0.384, 0, 0};
+// constexpr so the compiled-in Panda is regrouped by the compiler; the same function regroups a caller-supplied
+// inertial set at run time on the host (model_from_desc below).
+constexpr Model regroup_model(Model M) {
     for (int j = 6; j >= 1; --j) {
         LinkConst &c = M.L[j];
         LinkConst &p = M.L[j - 1];
@@ -130,6 +148,11 @@ constexpr Model make_model() {
     }
     return M;
 }
+constexpr Model make_model() {
+    Model M{};
+    for (int k = 0; k < 7; ++k) M.L[k] = raw_link_const(k);
+    return regroup_model(M);
+}
 constexpr Model kModel = make_model();
 constexpr LinkConst link_const(int k) { return kModel.L[k]; }
 
@@ -139,13 +162,74 @@ constexpr double kPayloadHz = kFlangeZ;
 constexpr double kPayloadJ = kPayloadR * kPayloadR + kFlangeZ * kFlangeZ;
 
 // panda_mod.urdf:127,153,179,205,231,257,283 (effort), lower/upper, velocity.
-__host__ __device__ constexpr double torque_limit(int i) { return i < 4 ? 87.0 : 12.0; }
+constexpr double torque_limit(int i) { return i < 4 ? 87.0 : 12.0; }
+
+// ---- where the inertial parameters come from ----------------------------------------------------------------
+// ConstParams: the compiled-in Panda (kModel) -- every parameter is an immediate, structural zeros vanish.
+// RtParams<T>: a caller-supplied inertial set (tcmp_rne_batch_model), regrouped on the host and passed to the
+// kernel by value (constant bank).  The DH geometry stays compile-time in both.
+struct ConstParams {};
+template <typename T> struct RtParams {
+    T jzz0;          // link 0 enters only through tau_0 = Jzz qdd_0
+    T l[5][7];       // links 1..5 after regrouping (m = hz = jyy = 0): hx hy jxx jxy jxz jyz jzz
+    T l6[10];        // link 6 + link8 + hand: m hx hy hz jxx jxy jxz jyy jyz jzz
+    T payload_hz;    // payload mass mp adds mp * payload_hz to hz ...
+    T payload_j;     // ... and mp * payload_j to jxx and jyy          (rne.py:181-188)
+    T tool_z;        // grasp-target height in the link-7 frame        (dyn mode)
+    T limit[6];      // torque limits of joints 1..6                   (joint 7 is never tested)
+};
+template <typename P> constexpr bool kIsConst = std::is_same<P, ConstParams>::value;
+
+// ---- host side of RtParams ------------------------------------------------------------------------------------
+// Caller's record -> per-link parameters about the link-frame origins, tail bodies folded, regrouped.
+inline Model model_from_desc(const tcmp_model &d) {
+    Model M{};
+    for (int k = 0; k < 7; ++k)
+        M.L[k] = make_link(kAlpha[k], kA[k], kD[k], d.mass[k], d.com[k][0], d.com[k][1], d.com[k][2], d.inertia[k][0],
+                           d.inertia[k][1], d.inertia[k][2], d.inertia[k][3], d.inertia[k][4], d.inertia[k][5]);
+    // link8 (DH row 8: pure translation d = 0.107 along z, rne.py:54) and the hand (identity on link8,
+    // rne.py:58-61) move rigidly with link 7: shift each to link 7's origin (parallel-axis) and add it.
+    LinkConst &L = M.L[6];
+    for (int b = 7; b < 9; ++b) {
+        const double m = d.mass[b], rx = d.com[b][0], ry = d.com[b][1], rz = d.com[b][2] + kFlangeZ;
+        const double *I = d.inertia[b];
+        const double r2 = rx * rx + ry * ry + rz * rz;
+        L.m += m;
+        L.hx += m * rx; L.hy += m * ry; L.hz += m * rz;
+        L.jxx += I[0] + m * (r2 - rx * rx);
+        L.jyy += I[3] + m * (r2 - ry * ry);
+        L.jzz += I[5] + m * (r2 - rz * rz);
+        L.jxy += I[1] - m * rx * ry;
+        L.jxz += I[2] - m * rx * rz;
+        L.jyz += I[4] - m * ry * rz;
+    }
+    return regroup_model(M);
+}
+
+template <typename T> inline RtParams<T> params_from_desc(const tcmp_model &d) {
+    const Model M = model_from_desc(d);
+    RtParams<T> P;
+    P.jzz0 = (T)M.L[0].jzz;
+    for (int k = 1; k <= 5; ++k) {
+        const LinkConst &L = M.L[k];
+        const double v[7] = {L.hx, L.hy, L.jxx, L.jxy, L.jxz, L.jyz, L.jzz};
+        for (int j = 0; j < 7; ++j) P.l[k - 1][j] = (T)v[j];
+    }
+    const LinkConst &L = M.L[6];
+    const double v6[10] = {L.m, L.hx, L.hy, L.hz, L.jxx, L.jxy, L.jxz, L.jyy, L.jyz, L.jzz};
+    for (int j = 0; j < 10; ++j) P.l6[j] = (T)v6[j];
+    P.payload_hz = (T)kFlangeZ;
+    P.payload_j = (T)(d.payload_radius * d.payload_radius + kFlangeZ * kFlangeZ);
+    P.tool_z = (T)(kFlangeZ + d.tool_z);
+    for (int i = 0; i < 6; ++i) P.limit[i] = (T)d.torque_limit[i];
+    return P;
+}
 
 template <typename T> struct V3 { T x, y, z; };
 
 // parent -> child frame:  E u,  E = Rz(theta)^T Rx(alpha)^T
 template <int ALPHA, typename T>
-__device__ __forceinline__ V3<T> rot_in(T c, T s, const V3<T> &u) {
+TCMP_FN V3<T> rot_in(T c, T s, const V3<T> &u) {
     T wy, wz;
     if constexpr (ALPHA == 0) { wy = u.y; wz = u.z; }
     else if constexpr (ALPHA > 0) { wy = u.z; wz = -u.y; }
@@ -154,16 +238,16 @@ __device__ __forceinline__ V3<T> rot_in(T c, T s, const V3<T> &u) {
 }
 // child -> parent frame:  R u,  R = Rx(alpha) Rz(theta)
 template <int ALPHA, typename T>
-__device__ __forceinline__ V3<T> rot_out(T c, T s, const V3<T> &u) {
+TCMP_FN V3<T> rot_out(T c, T s, const V3<T> &u) {
     const T wx = c * u.x - s * u.y, wy = s * u.x + c * u.y;
     if constexpr (ALPHA == 0) return {wx, wy, u.z};
     else if constexpr (ALPHA > 0) return {wx, -u.z, wy};
     else return {wx, u.z, -wy};
 }
 
-template <typename T> __device__ __forceinline__ void sincos_t(T x, T *s, T *c);
-template <> __device__ __forceinline__ void sincos_t<double>(double x, double *s, double *c) { sincos(x, s, c); }
-template <> __device__ __forceinline__ void sincos_t<float>(float x, float *s, float *c) { sincosf(x, s, c); }
+template <typename T> TCMP_FN void sincos_t(T x, T *s, T *c);
+template <> TCMP_FN void sincos_t<double>(double x, double *s, double *c) { sincos(x, s, c); }
+template <> TCMP_FN void sincos_t<float>(float x, float *s, float *c) { sincosf(x, s, c); }
 
 // Kinematic state carried down the chain, expressed in the current link frame.
 template <typename T> struct Kin {
@@ -175,7 +259,7 @@ template <typename T> struct Kin {
 // Forward step for link K >= 2 (and the generic form for K == 1 when the parent is a full Kin).
 // DYN == false is the static specialisation (qd = qdd = 0): only vd is propagated.
 template <int K, typename T, bool DYN>
-__device__ __forceinline__ void forward_link(T c, T s, T qd, T qdd, Kin<T> &k) {
+TCMP_FN void forward_link(T c, T s, T qd, T qdd, Kin<T> &k) {
     constexpr LinkConst L = link_const(K);
     static_assert(L.pz == 0.0, "generic forward step assumes a planar DH offset");
     V3<T> u = k.vd;
@@ -216,7 +300,7 @@ __device__ __forceinline__ void forward_link(T c, T s, T qd, T qdd, Kin<T> &k) {
 // HAS_M / HAS_HZ / HAS_JYY = false drop the terms of parameters that the regrouping made structurally zero.
 // Static: F = m vd, N = h x vd.
 template <typename T, bool DYN, bool HAS_M, bool HAS_HZ, bool HAS_JYY>
-__device__ __forceinline__ void link_wrench(const Kin<T> &k, T m, T hx, T hy, T hz, T jxx, T jxy, T jxz, T jyy,
+TCMP_FN void link_wrench(const Kin<T> &k, T m, T hx, T hy, T hz, T jxx, T jxy, T jxz, T jyy,
                                             T jyz, T jzz, V3<T> &F, V3<T> &N) {
     const V3<T> &vd = k.vd;
     if constexpr (HAS_HZ) N = {hy * vd.z - hz * vd.y, hz * vd.x - hx * vd.z, hx * vd.y - hy * vd.x};
@@ -247,17 +331,24 @@ __device__ __forceinline__ void link_wrench(const Kin<T> &k, T m, T hx, T hy, T 
     }
 }
 
-template <int K, typename T, bool DYN>
-__device__ __forceinline__ void link_wrench_const(const Kin<T> &k, V3<T> &F, V3<T> &N) {
-    constexpr LinkConst L = link_const(K);
-    link_wrench<T, DYN, L.m != 0.0, L.hz != 0.0, L.jyy != 0.0>(k, T(L.m), T(L.hx), T(L.hy), T(L.hz), T(L.jxx),
-                                                               T(L.jxy), T(L.jxz), T(L.jyy), T(L.jyz), T(L.jzz), F, N);
+template <int K, typename T, bool DYN, typename P>
+TCMP_FN void link_wrench_const(const P &p, const Kin<T> &k, V3<T> &F, V3<T> &N) {
+    if constexpr (kIsConst<P>) {
+        constexpr LinkConst L = link_const(K);
+        link_wrench<T, DYN, L.m != 0.0, L.hz != 0.0, L.jyy != 0.0>(k, T(L.m), T(L.hx), T(L.hy), T(L.hz), T(L.jxx),
+                                                                   T(L.jxy), T(L.jxz), T(L.jyy), T(L.jyz), T(L.jzz),
+                                                                   F, N);
+    } else {
+        static_assert(K >= 1 && K <= 5, "links 1..5 are the regrouped ones");
+        const T *l = p.l[K - 1];
+        link_wrench<T, DYN, false, false, false>(k, T(0), l[0], l[1], T(0), l[2], l[3], l[4], T(0), l[5], l[6], F, N);
+    }
 }
 
 // Backward step: fold child K's accumulated wrench (f, n, in frame K) into its parent's
 // (F, N in frame K-1):  f_p = F + R f,  n_p = N + R n + P x (R f).
 template <int K, typename T>
-__device__ __forceinline__ void backward_link(T c, T s, const V3<T> &f, const V3<T> &n, V3<T> &F, V3<T> &N) {
+TCMP_FN void backward_link(T c, T s, const V3<T> &f, const V3<T> &n, V3<T> &F, V3<T> &N) {
     constexpr LinkConst L = link_const(K);
     const V3<T> g = rot_out<L.alpha>(c, s, f);
     const V3<T> r = rot_out<L.alpha>(c, s, n);
@@ -282,19 +373,37 @@ __device__ __forceinline__ void backward_link(T c, T s, const V3<T> &f, const V3
 #ifndef TCMP_SINCOS6
 #define TCMP_SINCOS6 1
 #endif
+TCMP_FN int hi_word(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x);
+#else
+    int64_t b;
+    memcpy(&b, &x, 8);
+    return (int)(b >> 32);
+#endif
+}
+TCMP_FN int lo_word(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2loint(x);
+#else
+    int64_t b;
+    memcpy(&b, &x, 8);
+    return (int)(b & 0xffffffff);
+#endif
+}
 template <typename T>
-__device__ __forceinline__ void sincos6(const T (&q)[7], T (&s)[7], T (&c)[7]) {
+TCMP_FN void sincos6(const T (&q)[7], T (&s)[7], T (&c)[7]) {
     if constexpr (sizeof(T) == 8 && TCMP_SINCOS6) {
         bool fast = true;
 #pragma unroll
-        for (int j = 1; j < 7; ++j) fast = fast && ((__double2hiint((double)q[j]) & 0x7fffffff) < 0x40f86a00);  // |x| < 1e5
+        for (int j = 1; j < 7; ++j) fast = fast && ((hi_word((double)q[j]) & 0x7fffffff) < 0x40f86a00);  // |x| < 1e5
         if (fast) {
             double r[7], r2[7], ps[7], pc[7];
             int k[7];
 #pragma unroll
             for (int j = 1; j < 7; ++j) {
                 const double kt = fma((double)q[j], 0.63661977236758134308, 6755399441055744.0);  // rint via 1.5 * 2^52
-                k[j] = __double2loint(kt);
+                k[j] = lo_word(kt);
                 const double kd = kt - 6755399441055744.0;
                 double t = fma(-kd, 1.57079632673412561417e+00, (double)q[j]);
                 t = fma(-kd, 6.07710050630396597660e-11, t);
@@ -329,9 +438,9 @@ __device__ __forceinline__ void sincos6(const T (&q)[7], T (&s)[7], T (&c)[7]) {
     for (int j = 1; j < 7; ++j) sincos_t<T>(q[j], &s[j], &c[j]);
 }
 
-template <typename T, bool DYN, bool TOOL>
-__device__ __forceinline__ void rne_core(const T (&q)[7], const T (&qd)[7], const T (&qdd)[7], T mp_inertial,
-                                         T mp_tool, T (&tau)[7]) {
+template <typename T, bool DYN, bool TOOL, typename P = ConstParams>
+TCMP_FN void rne_core(const T (&q)[7], const T (&qd)[7], const T (&qdd)[7], T mp_inertial,
+                                         T mp_tool, T (&tau)[7], const P &p = P()) {
     T c[7], s[7];
     sincos6<T>(q, s, c);
 
@@ -341,7 +450,6 @@ __device__ __forceinline__ void rne_core(const T (&q)[7], const T (&qd)[7], cons
 
     // link 0: w = (0,0,qd0), wd = (0,0,qdd0), vd = (0,0,g) -- its own wrench only matters through
     // tau_0 = N_0.z = Jzz qdd0 (the w x Jw and h x vd terms have no z component).
-    constexpr LinkConst L0 = link_const(0);
     // link 1 (alpha = -pi/2, P = 0): E (0,0,z) = (-s z, -c z, 0)
     if constexpr (DYN) {
         k.w = {-s[1] * qd[0], -c[1] * qd[0], qd[1]};
@@ -349,31 +457,41 @@ __device__ __forceinline__ void rne_core(const T (&q)[7], const T (&qd)[7], cons
     }
     k.vd = {-s[1] * T(kGravity), -c[1] * T(kGravity), T(0)};
     if constexpr (TOOL && DYN) gv = k.vd;
-    link_wrench_const<1, T, DYN>(k, F[1], N[1]);
+    link_wrench_const<1, T, DYN>(p, k, F[1], N[1]);
 
 #define TCMP_FWD(K)                                                        \
     forward_link<K, T, DYN>(c[K], s[K], qd[K], qdd[K], k);                 \
     if constexpr (TOOL && DYN) gv = rot_in<link_const(K).alpha>(c[K], s[K], gv);
-    TCMP_FWD(2) link_wrench_const<2, T, DYN>(k, F[2], N[2]);
-    TCMP_FWD(3) link_wrench_const<3, T, DYN>(k, F[3], N[3]);
-    TCMP_FWD(4) link_wrench_const<4, T, DYN>(k, F[4], N[4]);
-    TCMP_FWD(5) link_wrench_const<5, T, DYN>(k, F[5], N[5]);
+    TCMP_FWD(2) link_wrench_const<2, T, DYN>(p, k, F[2], N[2]);
+    TCMP_FWD(3) link_wrench_const<3, T, DYN>(p, k, F[3], N[3]);
+    TCMP_FWD(4) link_wrench_const<4, T, DYN>(p, k, F[4], N[4]);
+    TCMP_FWD(5) link_wrench_const<5, T, DYN>(p, k, F[5], N[5]);
     TCMP_FWD(6)
 #undef TCMP_FWD
     {
-        constexpr LinkConst L = link_const(6);
-        const T m6 = T(L.m) + mp_inertial;
-        const T hz6 = T(L.hz) + mp_inertial * T(kPayloadHz);
-        const T jxx6 = T(L.jxx) + mp_inertial * T(kPayloadJ);
-        const T jyy6 = T(L.jyy) + mp_inertial * T(kPayloadJ);
-        link_wrench<T, DYN, true, true, true>(k, m6, T(L.hx), T(L.hy), hz6, jxx6, T(L.jxy), T(L.jxz), jyy6, T(L.jyz),
-                                              T(L.jzz), F[6], N[6]);
+        T tool_z;
+        if constexpr (kIsConst<P>) {
+            constexpr LinkConst L = link_const(6);
+            const T m6 = T(L.m) + mp_inertial;
+            const T hz6 = T(L.hz) + mp_inertial * T(kPayloadHz);
+            const T jxx6 = T(L.jxx) + mp_inertial * T(kPayloadJ);
+            const T jyy6 = T(L.jyy) + mp_inertial * T(kPayloadJ);
+            link_wrench<T, DYN, true, true, true>(k, m6, T(L.hx), T(L.hy), hz6, jxx6, T(L.jxy), T(L.jxz), jyy6,
+                                                  T(L.jyz), T(L.jzz), F[6], N[6]);
+            tool_z = T(kToolZ);
+        } else {
+            const T *l = p.l6;
+            link_wrench<T, DYN, true, true, true>(k, l[0] + mp_inertial, l[1], l[2], l[3] + mp_inertial * p.payload_hz,
+                                                  l[4] + mp_inertial * p.payload_j, l[5], l[6],
+                                                  l[7] + mp_inertial * p.payload_j, l[8], l[9], F[6], N[6]);
+            tool_z = p.tool_z;
+        }
         if constexpr (TOOL) {
             const V3<T> &g6 = DYN ? gv : k.vd;   // static: vd is exactly the rotated gravity vector
             const T fx = mp_tool * g6.x, fy = mp_tool * g6.y, fz = mp_tool * g6.z;
             F[6].x += fx; F[6].y += fy; F[6].z += fz;
-            N[6].x -= T(kToolZ) * fy;   // r x f, r = (0,0,kToolZ)
-            N[6].y += T(kToolZ) * fx;
+            N[6].x -= tool_z * fy;   // r x f, r = (0,0,tool_z)
+            N[6].y += tool_z * fx;
         }
     }
 
@@ -386,15 +504,24 @@ __device__ __forceinline__ void rne_core(const T (&q)[7], const T (&qd)[7], cons
     backward_link<2, T>(c[2], s[2], F[2], N[2], F[1], N[1]); tau[1] = N[1].z;
     // link 1 -> link 0: only n_0.z is needed; alpha_1 = -pi/2, P_1 = 0:  (R n).z = -(s n.x + c n.y)
     T t0 = -(s[1] * N[1].x + c[1] * N[1].y);
-    if constexpr (DYN) t0 += T(L0.jzz) * qdd[0];
+    if constexpr (DYN) {
+        if constexpr (kIsConst<P>) t0 += T(link_const(0).jzz) * qdd[0];
+        else t0 += p.jzz0 * qdd[0];
+    }
     tau[0] = t0;
 }
 
 // |tau_i| < limit_i for i in 0..5 (panda_primitives.py:182-183; joint 7 is never tested).
-template <typename T> __device__ __forceinline__ bool within_limits(const T (&tau)[7]) {
+template <typename T> TCMP_FN bool within_limits(const T (&tau)[7]) {
     bool ok = true;
 #pragma unroll
     for (int i = 0; i < 6; ++i) ok = ok && !(fabs(tau[i]) >= T(torque_limit(i)));
+    return ok;
+}
+template <typename T> TCMP_FN bool within_limits(const T (&tau)[7], const RtParams<T> &p) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ok = ok && !(fabs(tau[i]) >= p.limit[i]);
     return ok;
 }
 

@@ -173,6 +173,30 @@ int tcmp_rne_batch(int mode, int dtype, int64_t n, const void *q, const void *qd
     return TCMP_OK;
 }
 
+int tcmp_model_default(tcmp_model *out) {
+    if (!out) return fail(TCMP_ERR_INVALID_ARG, "model is NULL");
+    default_model_desc(out);
+    return TCMP_OK;
+}
+
+int tcmp_rne_batch_model(const tcmp_model *model, int mode, int dtype, int64_t n, const void *q, const void *qd,
+                         const void *qdd, const void *payload_mass, double payload_scalar, double payload_threshold,
+                         void *tau_out, uint8_t *feasible_out, void *stream) {
+    if (!model || mode == TCMP_MODE_BASE)   // base computes nothing, so no model enters
+        return tcmp_rne_batch(mode, dtype, n, q, qd, qdd, payload_mass, payload_scalar, payload_threshold, tau_out,
+                              feasible_out, stream);
+    if (int rc = check_common(mode, dtype, n)) return rc;
+    if (const char *why = model_desc_problem(*model)) return fail(TCMP_ERR_INVALID_ARG, "tcmp_model: %s", why);
+    if (n == 0) return TCMP_OK;
+    if (!q) return fail(TCMP_ERR_INVALID_ARG, "q is NULL");
+    if (!tau_out && !feasible_out) return fail(TCMP_ERR_INVALID_ARG, "both outputs are NULL");
+    if ((qd == nullptr) != (qdd == nullptr))
+        return fail(TCMP_ERR_INVALID_ARG, "qd and qdd must both be given or both be NULL");
+    TCMP_CUDA(launch_rne_batch_model(*model, mode, dtype, n, q, qd, qdd, payload_mass, payload_scalar,
+                                     payload_threshold, tau_out, feasible_out, (cudaStream_t)stream));
+    return TCMP_OK;
+}
+
 int tcmp_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
                            const void *payload_mass, double payload_scalar, double payload_threshold, void *tau_out,
                            int n_dest, void *const *dest_masks, int64_t dest_offset, void *stream) {

@@ -30,6 +30,13 @@ cudaError_t launch_rne_batch(int mode, int dtype, int64_t n, const void *q, cons
                              const void *payload_mass, double payload_scalar, double payload_threshold,
                              void *tau_out, uint8_t *feasible_out, cudaStream_t st);
 
+// model_kernels.cu: caller-supplied inertial set (mode BASE is handled by the caller: nothing to compute)
+cudaError_t launch_rne_batch_model(const tcmp_model &model, int mode, int dtype, int64_t n, const void *q,
+                                   const void *qd, const void *qdd, const void *payload_mass, double payload_scalar,
+                                   double payload_threshold, void *tau_out, uint8_t *feasible_out, cudaStream_t st);
+void default_model_desc(tcmp_model *out);
+const char *model_desc_problem(const tcmp_model &model);
+
 cudaError_t launch_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
                                      const void *payload_mass, double payload_scalar, double payload_threshold,
                                      void *tau_out, int n_dest, void *const *dest_masks, int64_t dest_offset,

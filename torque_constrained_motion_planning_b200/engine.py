@@ -116,12 +116,56 @@ def device_count() -> int:
     return n
 
 
+class InertialModel:
+    """``tcmp_model`` (include/tcmp.h): the masses, centres of mass, inertias, payload lever, tool height and torque
+    limits the torque test uses -- what the reference keeps in rne.py's module-level lists ``ms`` / ``cs`` /
+    ``inertia_matrices`` (rne.py:102,119,138).  One flat float64[99] record; the attributes are writable views::
+
+        m = InertialModel.default(); m.mass[8] = 1.1; m.com[8] = [0, 0, 0.06]      # another hand
+        tau, ok = torque_test_batch(q, qd, qdd, 1.0, model=m)
+    """
+    DOUBLES = 9 + 27 + 54 + 1 + 1 + 7
+
+    def __init__(self, record=None):
+        if record is None:
+            record = np.empty(self.DOUBLES)
+            check(load().tcmp_model_default(record.ctypes.data))
+        self.record = np.ascontiguousarray(record, dtype=np.float64).reshape(self.DOUBLES).copy()
+
+    @classmethod
+    def default(cls) -> "InertialModel":
+        return cls()
+
+    mass = property(lambda self: self.record[0:9])
+    com = property(lambda self: self.record[9:36].reshape(9, 3))
+    inertia = property(lambda self: self.record[36:90].reshape(9, 6))
+    torque_limit = property(lambda self: self.record[92:99])
+
+    @property
+    def payload_radius(self) -> float:
+        return float(self.record[90])
+
+    @payload_radius.setter
+    def payload_radius(self, v: float) -> None:
+        self.record[90] = v
+
+    @property
+    def tool_z(self) -> float:
+        return float(self.record[91])
+
+    @tool_z.setter
+    def tool_z(self, v: float) -> None:
+        self.record[91] = v
+
+
 def torque_test_batch(q, qd=None, qdd=None, payload_mass=0.0, mode: str = "rne", dtype: str = "f64",
                       payload_threshold: float = PAYLOAD_THRESHOLD_TEST, want_tau: bool = True,
-                      want_mask: bool = True, workspace: Optional[Workspace] = None, out_tau=None, out_mask=None):
+                      want_mask: bool = True, workspace: Optional[Workspace] = None, out_tau=None, out_mask=None,
+                      model: Optional[InertialModel] = None):
     """Batched torque test (tcmp_rne_batch).  q/qd/qdd ``[7][n]``; payload_mass scalar or ``[n]``.
     Returns ``(tau [7][n] or None, feasible uint8 [n] or None)``.  Device path only: ``out_tau`` / ``out_mask``
-    are optional preallocated CUDA tensors to write into (no allocation on the call)."""
+    are optional preallocated CUDA tensors to write into (no allocation on the call).  ``model``: another inertial
+    set than the compiled-in Panda (tcmp_rne_batch_model); host arrays are then staged through torch."""
     lib = load()
     if not (want_tau or want_mask):
         raise ValueError("nothing to compute")
@@ -132,6 +176,13 @@ def torque_test_batch(q, qd=None, qdd=None, payload_mass=0.0, mode: str = "rne",
         scalar = float(payload_mass)
     else:
         pm = payload_mass
+    if model is not None and not _is_cuda_tensor(q):
+        torch = _torch()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        up = lambda a: None if a is None else torch.as_tensor(_as_host(a, dtype, np.shape(a)), device=dev)
+        tau, mask = torque_test_batch(up(q), up(qd), up(qdd), scalar if pm is None else up(pm), mode, dtype,
+                                      payload_threshold, want_tau, want_mask, model=model)
+        return (None if tau is None else tau.cpu().numpy()), (None if mask is None else mask.cpu().numpy())
     if _is_cuda_tensor(q):
         torch = _torch()
         dev = q.device
@@ -144,8 +195,13 @@ def torque_test_batch(q, qd=None, qdd=None, payload_mass=0.0, mode: str = "rne",
                 if want_tau else None
             mask = (out_mask if out_mask is not None else torch.empty((n,), dtype=torch.uint8, device=dev)) \
                 if want_mask else None
-            check(lib.tcmp_rne_batch(MODE[mode], DTYPE[dtype], n, _ptr(qt), _ptr(qdt), _ptr(qddt), _ptr(pmt), scalar,
-                                     float(payload_threshold), _ptr(tau), _ptr(mask), _stream_ptr()))
+            if model is None:
+                check(lib.tcmp_rne_batch(MODE[mode], DTYPE[dtype], n, _ptr(qt), _ptr(qdt), _ptr(qddt), _ptr(pmt),
+                                         scalar, float(payload_threshold), _ptr(tau), _ptr(mask), _stream_ptr()))
+            else:
+                check(lib.tcmp_rne_batch_model(model.record.ctypes.data, MODE[mode], DTYPE[dtype], n, _ptr(qt),
+                                               _ptr(qdt), _ptr(qddt), _ptr(pmt), scalar, float(payload_threshold),
+                                               _ptr(tau), _ptr(mask), _stream_ptr()))
         return tau, mask
     ws = workspace or default_workspace()
     qa = _as_host(q, dtype, (7, n))

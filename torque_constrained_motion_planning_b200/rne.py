@@ -8,6 +8,10 @@ state between calls exactly as the reference's closures expect (panda_primitives
 New: ``rne_batch`` evaluates many states per call ([7][n] arrays, CUDA tensors or NumPy) and takes
 the payload as an argument instead of module state, so it is re-entrant.
 
+The reference keeps its inertial tables in the module-level lists ``ms`` / ``cs`` / ``inertia_matrices``
+(rne.py:102,119,138), which a user can edit in place.  The equivalent here is ``set_inertial_model(model)`` with an
+``engine.InertialModel`` (tcmp_model); ``get_ms_global()`` reports the masses in the reference's 10-entry layout.
+
 Every call runs on the GPU; a scalar ``rne()`` is a batch of one.
 """
 from __future__ import annotations
@@ -19,6 +23,23 @@ from ._lib import PAYLOAD_THRESHOLD_RAW
 
 _has_payload = False
 _payload_mass = 0.0
+_model = None   # engine.InertialModel, or None = the compiled-in Panda
+
+
+def set_inertial_model(model) -> None:
+    """Use another inertial set (engine.InertialModel) for rne() / rne_batch(); None restores the stock Panda."""
+    global _model
+    _model = model
+
+
+def get_inertial_model():
+    return _model
+
+
+def get_ms_global() -> list:
+    """rne.py:154-156: link1..7, link8, hand, payload link (0.0 while no payload is attached)."""
+    mass = (_model or engine.InertialModel.default()).mass
+    return [float(m) for m in mass] + [_payload_mass if _has_payload else 0.0]
 
 
 def get_has_payload() -> bool:
@@ -49,12 +70,14 @@ def rne(q, qd, qdd) -> np.ndarray:
     """Joint torques (7,) of the Panda + hand (+ current payload) -- rne.py:198-254."""
     col = lambda v: np.asarray(v, dtype=np.float64).reshape(-1)[:7].reshape(7, 1)
     tau, _ = engine.torque_test_batch(col(q), col(qd), col(qdd), _payload_mass if _has_payload else 0.0,
-                                      mode="rne", payload_threshold=PAYLOAD_THRESHOLD_RAW, want_mask=False)
+                                      mode="rne", payload_threshold=PAYLOAD_THRESHOLD_RAW, want_mask=False,
+                                      model=_model)
     return tau[:, 0].copy()
 
 
-def rne_batch(q, qd=None, qdd=None, payload_mass=0.0, dtype="f64"):
+def rne_batch(q, qd=None, qdd=None, payload_mass=0.0, dtype="f64", model=None):
     """Torques [7][n] for states [7][n]; payload attached iff mass > 0 (the raw rne.py rule)."""
     tau, _ = engine.torque_test_batch(q, qd, qdd, payload_mass, mode="rne", dtype=dtype,
-                                      payload_threshold=PAYLOAD_THRESHOLD_RAW, want_mask=False)
+                                      payload_threshold=PAYLOAD_THRESHOLD_RAW, want_mask=False,
+                                      model=model if model is not None else _model)
     return tau
