@@ -17,17 +17,6 @@ namespace tcmp {
 // the gathered buffer of EVERY rank (peer pointers mapped over NVLink/NVSwitch, CUDA IPC) at
 // dest_offset + i.  1 B/state/peer of NVLink traffic rides under an FP64-bound kernel; no extra launch,
 // no host-side collective call (which costs more CPU time than this 63 us kernel runs).
-#ifndef TCMP_PREFETCH
-#define TCMP_PREFETCH 0   // 0 = off (default: measured 9 % SLOWER on, ptxas goes from 126 to 202 registers), 1 = prefetch.global.L1, 2 = .L2
-#endif
-__device__ __forceinline__ void prefetch_line(const void *p) {
-#if TCMP_PREFETCH == 2
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
-
 #ifndef TCMP_PDL
 #define TCMP_PDL 1
 #endif
@@ -76,8 +65,8 @@ rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T
 #if TCMP_DOUBLE_BUFFER
     // Register double buffering: the NEXT grid-stride state's 22 inputs are loaded before the current state's
     // recursion starts, so a warp never sits in a long-scoreboard stall with nothing to issue (ncu: 1.06 -> 0.14
-    // long-scoreboard stalls per issue).  TCMP_DOUBLE_BUFFER == 2 ping-pongs two register sets (loop unrolled
-    // twice) instead of copying next -> current after every state.
+    // long-scoreboard stalls per issue).  (Ping-ponging two register sets instead of copying next -> current spills
+    // and is 16 % slower; prefetch.global of the next rows costs 76 registers and 9 % -- see DESIGN.md 6b.)
     const I stride = (I)(gridDim.x * blockDim.x);
     I i = (I)(blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= n) return;
@@ -109,22 +98,6 @@ rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T
     };
     T qa[7], va[7], aa[7], ma, qb[7], vb[7], ab[7], mb;
     load(i, qa, va, aa, ma);
-#if TCMP_DOUBLE_BUFFER == 2
-    for (;;) {
-        I nx = i + stride;
-        bool more = nx < n;
-        if (more) load(nx, qb, vb, ab, mb);
-        consume(i, qa, va, aa, ma);
-        if (!more) break;
-        i = nx;
-        nx = i + stride;
-        more = nx < n;
-        if (more) load(nx, qa, va, aa, ma);
-        consume(i, qb, vb, ab, mb);
-        if (!more) break;
-        i = nx;
-    }
-#else
     for (;;) {
         const I nx = i + stride;
         const bool more = nx < n;
@@ -139,31 +112,11 @@ rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T
         ma = mb;
         i = nx;
     }
-#endif
 }
 #else
     const I stride = (I)(gridDim.x * blockDim.x);
     for (I i = (I)(blockIdx.x * blockDim.x + threadIdx.x); i < n; i += stride) {
         T qs[7], vs[7], as[7], tau[7];
-#if TCMP_PREFETCH
-        // ncu (round 1): 0.92 long-scoreboard stalls per issued instruction -- each state starts by waiting
-        // ~800 cycles for its 22 DRAM loads with only ~3 warps per scheduler to cover them.  Prefetching the
-        // NEXT state's rows while this one computes costs no registers and turns those loads into cache hits.
-        {
-            const I nx = i + stride;
-            if (nx < n) {
-#pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    prefetch_line(q + j * n + nx);
-                    if constexpr (DYN) {
-                        prefetch_line(qd + j * n + nx);
-                        prefetch_line(qdd + j * n + nx);
-                    }
-                }
-                if (payload_mass) prefetch_line(payload_mass + nx);
-            }
-        }
-#endif
 #pragma unroll
         for (int j = 0; j < 7; ++j) qs[j] = __ldcs(q + j * n + i);
         if constexpr (DYN) {
