@@ -131,7 +131,7 @@ static cudaError_t launch_edge_t(int64_t n_edges, int W, const void *qa, const v
     double interval, step;
     linspace_params(W, &interval, &step);
     auto kern = edge_kernel<T, DYN, TOOL>;
-    const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, n_edges * 32);
+    const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, n_edges * 32, kEdgeWaves);
     kern<<<grid, 128, 0, st>>>(n_edges, W, interval, step, (const T *)qa, (const T *)qb, (T)ps, (T)pt, ff, dests);
     return cudaGetLastError();
 }

@@ -155,12 +155,12 @@ cudaError_t launch_ik_select(int64_t n, const double *rot9, const double *trans3
     }
     const int check = mode != TCMP_MODE_BASE;
     if (mode == TCMP_MODE_DYN) {
-        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<true>), kSelWarps * 32, n * 32);
+        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<true>), kSelWarps * 32, n * 32, kSelWaves);
         ik_select_kernel<true><<<grid, kSelWarps * 32, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref,
                                                      ref_broadcast, lim, check, mass, payload_threshold, use_max_norm,
                                                      best_q, best_cost, n_valid);
     } else {
-        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<false>), kSelWarps * 32, n * 32);
+        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<false>), kSelWarps * 32, n * 32, kSelWaves);
         ik_select_kernel<false><<<grid, kSelWarps * 32, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref,
                                                       ref_broadcast, lim, check, mass, payload_threshold, use_max_norm,
                                                       best_q, best_cost, n_valid);

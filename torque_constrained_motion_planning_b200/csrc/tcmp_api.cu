@@ -40,11 +40,11 @@ int sm_count() {
     return cached[dev];
 }
 
-int grid_for(const void *kernel, int block, int64_t n_threads_needed) {
+int grid_for(const void *kernel, int block, int64_t n_threads_needed, int waves) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm <= 0)
         per_sm = 1;
-    const int64_t full = (int64_t)sm_count() * per_sm;
+    const int64_t full = (int64_t)sm_count() * per_sm * (waves > 0 ? waves : 1);
     int64_t want = (n_threads_needed + block - 1) / block;
     if (want < 1) want = 1;
     return (int)(want < full ? want : full);

@@ -7,10 +7,16 @@
 
 namespace tcmp {
 
-// Persistent-style grid: enough CTAs to fill every SM at the kernel's occupancy, never more
-// than the work needs.  148 SMs on B200; the count is read from the device so a grid is always
-// a whole number of waves.
-int grid_for(const void *kernel, int block, int64_t n_threads_needed);
+// Persistent-style grid: `waves` x enough CTAs to fill every SM at the kernel's occupancy, never more than the
+// work needs.  148 SMs on B200; the count is read from the device so a grid is always a whole number of waves.
+// One wave minimises CTA launches; a few waves let retiring CTAs be replaced, which matters when units differ in
+// cost (edges stop at their first failing waypoint, IK solves die at different gates) or warps run ahead.
+int grid_for(const void *kernel, int block, int64_t n_threads_needed, int waves = 1);
+// Measured (profiles/r01/ab_variants_aux_waves.log): edges +7 % and goal-IK selection +8 % at 16 waves; the IK
+// sweep kernel LOSES with more waves (every retiring CTA flushes a partly filled survivor queue), as does the
+// single-buffered model kernel, so those stay at one.
+constexpr int kEdgeWaves = 16;
+constexpr int kSelWaves = 16;
 int sm_count();
 
 // out[i] = v for i < n (used by the `base` torque test, which is constant-true).
