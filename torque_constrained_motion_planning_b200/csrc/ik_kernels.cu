@@ -29,55 +29,9 @@ constexpr int kSolRow = 57;
 
 constexpr int kIkBlock = 64;   // 2 warps x 32 rows x 57 doubles = 29 KB of static shared memory (< 48 KB)
 
-template <bool WRITE_SOLS>
-__global__ void __launch_bounds__(kIkBlock)
-ik_kernel(int64_t n, int n_free, int free_broadcast, const double *__restrict__ rot9,
-          const double *__restrict__ trans3, const double *__restrict__ free_vals, double *__restrict__ sols_out,
-          int32_t *__restrict__ count_out, uint8_t *__restrict__ status_out) {
-    __shared__ double stage[WRITE_SOLS ? (kIkBlock / 32) * 32 * kSolRow : 1];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t total = n * n_free;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t rounds = (total + stride - 1) / stride;
-    for (int64_t r = 0; r < rounds; ++r) {
-        const int64_t s = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        const bool live = s < total;
-        double *row = WRITE_SOLS ? &stage[(wib * 32 + lane) * kSolRow] : nullptr;
-        if (live) {
-            const int64_t p = s / n_free;
-            const int f = (int)(s - p * n_free);
-            double R[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) R[i] = __ldg(rot9 + i * n + p);
-            const double j6 = free_broadcast ? __ldg(free_vals + f) : __ldg(free_vals + (int64_t)f * n + p);
-            Pose P;
-            prepare_pose(R, __ldg(trans3 + p), __ldg(trans3 + n + p), __ldg(trans3 + 2 * n + p), j6, P);
-            Emit out;
-            out.sols = row;
-            out.count = 0;
-            out.status = 0;
-            solve_one(P, out);
-            if (WRITE_SOLS)
-                for (int k = (out.count < 8 ? out.count : 8) * 7; k < 56; ++k) row[k] = 0.0;
-            count_out[s] = out.count;
-            if (status_out) status_out[s] = (uint8_t)out.status;
-        }
-        if (WRITE_SOLS) {
-            __syncwarp();
-            const int64_t warp_first = s - lane;                         // first solve of this warp's span
-            const int64_t span = (total - warp_first) < 32 ? (total - warp_first) : 32;
-            if (span > 0) {
-                double *dst = sols_out + warp_first * 56;
-                const double *src = &stage[wib * 32 * kSolRow];
-                for (int idx = lane; idx < (int)span * 56; idx += 32) dst[idx] = src[(idx / 56) * kSolRow + idx % 56];
-            }
-            __syncwarp();
-        }
-    }
-}
-
-// Compacting form (ncu on the kernel above: 14 of 32 lanes active, because ~45 % of a sweep's solves fail the
-// solver's first gate and return at once while their warp-mates run all 8 branches).  Each warp walks chunks of 32
+// Compacting kernel.  (The first build mapped one lane to one solve for its whole life; ncu showed 14 of 32 lanes
+// active, because ~45 % of a sweep's solves fail the solver's first gate and return at once while their warp-mates
+// run all 8 branches -- profiles/r01/ncu_full_ik_kernel_raw.csv.)  Each warp walks chunks of 32
 // consecutive solves; lanes SCREEN their solve (pose reduction + the j3 gate), finish the rejected ones on the spot
 // and push the survivors' indices into a per-warp shared-memory queue (ballot / popc prefix).  Whenever 32
 // survivors are queued, the warp solves them with every lane busy.  Solution sets are staged in shared memory and
@@ -224,10 +178,6 @@ fk_kernel(int64_t n, const double *__restrict__ q, double *__restrict__ trans3, 
 cudaError_t launch_ik_batch(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
                             int n_free, int free_broadcast, double *sols_out, int32_t *count_out,
                             uint8_t *status_out, cudaStream_t st) {
-#ifndef TCMP_IK_COMPACT
-#define TCMP_IK_COMPACT 1
-#endif
-#if TCMP_IK_COMPACT
     if (sols_out) {
         const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel_compact<true>), ik::kIkBlock, n * n_free);
         ik::ik_kernel_compact<true><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals,
@@ -237,17 +187,6 @@ cudaError_t launch_ik_batch(int64_t n, const double *rot9, const double *trans3,
         ik::ik_kernel_compact<false><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals,
                                                                     sols_out, count_out, status_out);
     }
-#else
-    if (sols_out) {
-        const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel<true>), ik::kIkBlock, n * n_free);
-        ik::ik_kernel<true><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out,
-                                                  count_out, status_out);
-    } else {
-        const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel<false>), ik::kIkBlock, n * n_free);
-        ik::ik_kernel<false><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out,
-                                                   count_out, status_out);
-    }
-#endif
     return cudaGetLastError();
 }
 
