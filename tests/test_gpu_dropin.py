@@ -59,6 +59,32 @@ def test_rne_module_with_another_inertial_set():
     assert np.abs(R.rne(Q_HOME, z, z) - oracle.rne(Q_HOME, z, z)).max() < 1e-9
 
 
+def test_remaining_reference_named_helpers():
+    """rne.get_cs_global / get_inertia_matricies, ikfast.ikfast_forward_kinematics / check_solution,
+    panda_primitives.test_path_torque_constraint."""
+    from torque_constrained_motion_planning_b200 import ikfast, panda_primitives as PP, rne as R, utils
+    assert len(R.get_cs_global()) == 10 and len(R.get_inertia_matricies()) == 9
+    R.add_payload(None, 2.0)
+    I = R.get_inertia_matricies()
+    assert len(I) == 10 and np.allclose(np.diag(I[9]), [2.0 * 0.165 ** 2, 2.0 * 0.165 ** 2, 0.0])
+    R.remove_payload()
+    pose = ikfast.ikfast_forward_kinematics(None, ikfast.PANDA_INFO, None, Q_HOME)
+    if oracle.have_ref():
+        trans, rot = oracle.ref_fk_batch(np.asarray(Q_HOME, dtype=float).reshape(7, 1))
+        assert np.abs(np.asarray(pose[0]) - trans[:, 0]).max() < 1e-12
+    assert ikfast.check_solution(None, list(range(7)), Q_HOME, None, pose)
+    moved = list(Q_HOME); moved[1] += 0.01
+    assert not ikfast.check_solution(None, list(range(7)), moved, None, pose)
+    q, _, _, _ = sample_states(300, seed=14)
+    path = [tuple(c) for c in q.T]
+    for mass in (0.0, 5.0):
+        test_fn = PP.get_torque_limits_not_exceded_test_v4(utils.Problem(None, [], None, mass, 5, "rne"))
+        _, ok = oracle.torque_test_batch("rne", q, None, None, mass)
+        assert PP.test_path_torque_constraint(None, None, None, path, mass, None, test_fn) == (not ok.all())
+        good = [p for p, o in zip(path, ok) if o]
+        assert PP.test_path_torque_constraint(None, None, None, good, mass, None, test_fn) is False
+
+
 def test_ikfast_module_surface():
     from torque_constrained_motion_planning_b200 import ikfast_panda_arm as ik
     pos, rot = ik.get_fk(list(Q_HOME))

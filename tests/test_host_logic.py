@@ -122,6 +122,40 @@ def test_rrt_star_matches_reference_tree_growth(seed):
         assert len(out_new[0]) > 2
 
 
+def test_plain_rrt_star_and_safe_path():
+    """The torque-blind planner (rrt_star.py:99-149) and safe_path (:82-88): batched prefix == serial prefix, and
+    the returned path is collision-free, starts at start and ends at the goal."""
+    joints = list(range(7))
+    res = 0.1 * np.ones(7)
+    col = collision.get_collision_fn(obstacles=collision.hiro_scene())
+    serial = lambda q: col(q)                     # plain callable: no .batch -> the reference's loop
+    dist = utils.get_distance_fn(None, joints, weights=np.reciprocal(res))
+    ext = utils.get_extend_fn(None, joints, resolutions=res)
+    start = tuple(panda_model.TOP_HOLDING_LEFT_ARM)
+    goal = (0.6, -0.2, 0.3, -1.9, 0.1, 1.8, 0.9)
+    into_table = (0.0, 1.7, 0.0, -0.8, 0.0, 3.0, 0.0)          # hand below the table top
+    for a, b in ((start, goal), (start, into_table)):
+        assert rrt_star.safe_path(ext(a, b), col) == rrt_star.safe_path(ext(a, b), serial)
+    assert len(rrt_star.safe_path(ext(start, into_table), col)) < len(list(ext(start, into_table)))
+    random.seed(4)
+    samp = utils.get_sample_fn(None, joints, rng=np.random.RandomState(4))
+    path = rrt_star.rrt_star(start, goal, dist, samp, ext, col, radius=0.5, max_iterations=60)
+    assert path is not None and np.allclose(path[0], start) and np.allclose(path[-1], goal)
+    assert not np.asarray(col.batch(path)).any()
+    assert rrt_star.rrt_star(into_table, goal, dist, samp, ext, col, radius=0.5, max_iterations=5) is None
+    assert rrt_star.elapsed_time(0.0) > 0
+
+
+def test_small_boundary_helpers():
+    from torque_constrained_motion_planning_b200 import franka_ik_fast, ikfast
+    assert franka_ik_fast.get_joint_distances([0] * 7, [1] * 7) == pytest.approx(1.0)
+    assert franka_ik_fast.get_tool_from_ik(None, "right") == ((0.0, 0.0, 0.0), (0.0, 0.0, 0.0, 1.0))
+    assert ik_utils.get_ik_limits(None, 6) == (-2.8973, 2.8973)
+    assert ik_utils.get_ik_limits(None, 6, limits=ik_utils.USE_CURRENT, current_conf=[0, 0, 0, 0, 0, 0, 0.3]) == (0.3, 0.3)
+    assert ik_utils.get_ik_limits(None, 6, limits=(-1, 1)) == (-1, 1)
+    assert ikfast.get_ik_joints() == list(range(7)) and ikfast.get_module_name() == "ikfast_panda_arm"
+
+
 def test_pose_algebra_round_trip():
     rng = np.random.default_rng(2)
     for _ in range(50):

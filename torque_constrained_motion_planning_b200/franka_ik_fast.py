@@ -16,6 +16,18 @@ info = {"left": PANDA_LEFT_INFO, "right": PANDA_RIGHT_INFO}
 FRANKA_URDF = "models/panda_mod.urdf"
 
 
+def get_tool_from_ik(robot=None, arm="right"):
+    """franka_ik_fast.py:30-34: pose of the IK frame (``panda_grasptarget``) in the tool frame; both names denote
+    the same link in this robot (utils.py PANDA_TOOL_FRAME, IK_FRAME['right']), so it is the identity."""
+    return (0.0, 0.0, 0.0), (0.0, 0.0, 0.0, 1.0)
+
+
+def get_joint_distances(current_config, new_config):
+    """Mean squared joint difference (franka_ik_fast.py:39-44)."""
+    n = len(new_config)
+    return sum((new_config[i] - current_config[i]) ** 2 / n for i in range(n))
+
+
 def get_ik_generator(robot, arm, gripper_link, gripper_pose, max_attempts=25, max_time=1.3, current_conf=None):
     """franka_ik_fast.py:36-37 (the reference hard-codes 25 attempts / 1.3 s regardless of the arguments)."""
     return ikfast_inverse_kinematics(robot, info[arm], gripper_link, tool_pose_to_link8(gripper_pose),

@@ -105,6 +105,18 @@ def ik_sweep(pose, current_free, max_attempts=25, rng=None, lower=Q_LOWER, upper
     return out
 
 
+def get_ik_limits(robot, joint, limits=USE_ALL, current_conf=None):
+    """ik_utils.py:34-40: the sampling interval of a free joint -- its URDF limits (USE_ALL), its current value
+    (USE_CURRENT; from ``current_conf``, default the home configuration) or the pair given."""
+    if limits is USE_ALL:
+        return float(Q_LOWER[joint]), float(Q_UPPER[joint])
+    if limits is USE_CURRENT:
+        from .panda_model import TOP_HOLDING_LEFT_ARM
+        value = float((TOP_HOLDING_LEFT_ARM if current_conf is None else current_conf)[joint])
+        return value, value
+    return limits
+
+
 def select_solution(body, joints, solutions, nearby_conf=USE_ALL, **kwargs):
     if not solutions:
         return None

@@ -25,6 +25,38 @@ from .panda_model import Q_LOWER, Q_UPPER, TOP_HOLDING_LEFT_ARM
 INF = float("inf")
 
 
+def get_module_name(ikfast_info=PANDA_INFO):
+    return "{}".format(ikfast_info.module_name)   # ikfast.py:24-25
+
+
+def get_ik_joints(robot=None, ikfast_info=PANDA_INFO, tool_link=None):
+    """The 6 + len(free_joints) joints between base and end-effector link (ikfast.py:74-89): the seven arm joints."""
+    return list(range(7))
+
+
+def ikfast_forward_kinematics(robot, ikfast_info, tool_link, conf=None, use_ikfast=True):
+    """Pose ``(point, quaternion xyzw)`` of ``panda_link8`` in ``panda_link0`` for ``conf`` (ikfast.py:105-133 with
+    world_from_base = tool_from_ee = identity: there is no PyBullet scene to read them from).  ``conf`` defaults
+    to the reference's home configuration."""
+    from .ik_utils import compute_forward_kinematics
+    conf = TOP_HOLDING_LEFT_ARM if conf is None else conf
+    return compute_forward_kinematics(import_ikfast(ikfast_info).get_fk, list(conf))
+
+
+def check_solution(robot, joints, conf, tool_link, target_pose, tolerance=1e-6):
+    """ikfast.py:93-102: does FK(conf) reproduce ``target_pose`` (link8 in link0) to ``tolerance``?"""
+    from .ik_utils import matrix_from_quat
+    point, quat = ikfast_forward_kinematics(robot, PANDA_INFO, tool_link, conf)
+    pos_distance = float(np.linalg.norm(np.asarray(point) - np.asarray(target_pose[0])))
+    R = np.asarray(matrix_from_quat(quat)).T @ np.asarray(matrix_from_quat(target_pose[1]))
+    ori_distance = float(np.arccos(np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)))
+    valid = pos_distance <= tolerance and ori_distance <= tolerance
+    if not valid:
+        print("IKFast warning! | Valid: {} | Position error: {:.3e} | Orientation error: {:.3e}".format(
+            valid, pos_distance, ori_distance))
+    return valid
+
+
 def import_ikfast(ikfast_info=PANDA_INFO):
     return importlib.import_module("." + ikfast_info.module_name, package=__package__)
 

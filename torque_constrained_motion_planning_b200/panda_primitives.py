@@ -118,6 +118,23 @@ _FACTORIES = {"rne": get_torque_limits_not_exceded_test_v4, "dyn": get_torque_li
               "base": get_torque_limits_not_exceded_test_base, "nov": get_torque_limits_not_exceded_test_v3_nov}
 
 
+def test_path_torque_constraint(robot, arm, joints, path, mass, r, test_fn):
+    """panda_primitives.py:284-293: True iff some configuration of ``path`` EXCEEDS the torque limits.  The reference
+    moves the PyBullet robot through the path and calls ``test_fn(arm, ptotalMass=mass, pcomR=r)`` per
+    configuration; here the whole path is one batched torque test (``test_fn.batch``) when the test offers it."""
+    batch = getattr(test_fn, "batch", None)
+    if batch is not None:
+        exceeded = not bool(np.asarray(batch(list(path), ptotalMass=mass), dtype=bool).all())
+    else:
+        exceeded = any(not test_fn(conf, ptotalMass=mass) for conf in path)
+    if exceeded:
+        print("conf torques exceded in path")
+    return exceeded
+
+
+test_path_torque_constraint.__test__ = False   # a reference-named helper, not a pytest case
+
+
 def get_dynamics_fn_v5(problem, resolutions):
     num_joints = 7
 

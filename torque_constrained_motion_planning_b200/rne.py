@@ -42,6 +42,23 @@ def get_ms_global() -> list:
     return [float(m) for m in mass] + [_payload_mass if _has_payload else 0.0]
 
 
+def get_cs_global() -> list:
+    """rne.py:162-164: centres of mass, 10 entries (the payload link's stays at the origin, rne.py:181-188)."""
+    com = (_model or engine.InertialModel.default()).com
+    return [np.array(c) for c in com] + [np.zeros(3)]
+
+
+def get_inertia_matricies() -> list:
+    """rne.py:142-144 (sic): 3x3 inertias about the centres of mass; the payload's is appended while one is
+    attached, as add_payload does (rne.py:186-187)."""
+    mdl = _model or engine.InertialModel.default()
+    out = [np.array([[i[0], i[1], i[2]], [i[1], i[3], i[4]], [i[2], i[4], i[5]]]) for i in mdl.inertia]
+    if _has_payload:
+        r2 = mdl.payload_radius ** 2
+        out.append(np.diag([_payload_mass * r2, _payload_mass * r2, 0.0]))
+    return out
+
+
 def get_has_payload() -> bool:
     return _has_payload
 

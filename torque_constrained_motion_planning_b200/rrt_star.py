@@ -8,7 +8,8 @@ is one batch: if the predicates expose ``.batch`` (ours do), all configurations 
 one vectorised collision call and ONE torque-kernel launch, and the safe prefix is cut at the first
 failure of either -- the same result as the serial loop.
 
-``strict_reference=True`` (default) keeps the reference's observable quirks: the time
+``strict_reference=True`` (default) keeps the reference's observable quirks (with ``informed=True``
+that includes its endless loop once a straight-line solution exists -- callers pass ``informed=False``): the time
 bound is ineffective (``t0 - time()`` is never positive, :159), the neighbour set is a one-shot
 iterator so only the first rewiring loop ever runs (:183-198), ``radius`` is compared as given
 (a one-element list, panda_primitives.py:346).  ``strict_reference=False`` runs both rewiring loops.
@@ -95,6 +96,12 @@ class OptimalNode(object):
     __str__ = __repr__
 
 
+def elapsed_time(start_time):
+    """Seconds since ``start_time`` (rrt_star.py:6-7; the reference's body calls ``time.time()`` on the imported
+    FUNCTION and raises AttributeError -- which also kills its plain ``rrt_star`` at the first progress print)."""
+    return time() - start_time
+
+
 def _first_failure(flags_bad):
     flags_bad = np.asarray(flags_bad, dtype=bool)
     return int(np.argmax(flags_bad)) if flags_bad.any() else len(flags_bad)
@@ -146,6 +153,66 @@ def safe_path_force_aware(sequence, collision, torque):
     if keep:
         keep = min(keep, _first_failure(~np.asarray(tq_batch(configs[:keep]), dtype=bool)))
     return configs[:keep]
+
+
+def safe_path(sequence, collision):
+    """Longest collision-free prefix of ``sequence`` (rrt_star.py:82-88); one vectorised call when the predicate
+    offers ``.batch``."""
+    configs = list(sequence)
+    col_batch = getattr(collision, "batch", None)
+    if col_batch is not None and configs:
+        return configs[:_first_failure(col_batch(configs))]
+    keep = 0
+    for q in configs:
+        if collision(q):
+            break
+        keep += 1
+    return configs[:keep]
+
+
+def rrt_star(start, goal, distance, sample, extend, collision, radius, max_time=INF, max_iterations=INF,
+             goal_probability=.4, informed=True):
+    """The torque-blind planner (rrt_star.py:99-149): RRT* over collision-free edges, returns the list of
+    configurations or None.  Same sampling / goal-bias / informed-rejection / rewiring rules as the reference's
+    source; its progress print (which crashes the reference, see ``elapsed_time``) is dropped, the time bound is
+    a real one, rejected samples count as iterations, and both rewiring passes run."""
+    if collision(start) or collision(goal):
+        return None
+    tree = [OptimalNode(start)]
+    goal_node = None
+    began = time()
+    it = 0
+    while elapsed_time(began) < max_time and it < max_iterations:
+        aim_at_goal = goal_node is None and (it == 0 or random() < goal_probability)
+        target = goal if aim_at_goal else sample()
+        it += 1     # before the informed rejection: the reference counts only accepted samples (:110-115), so once a
+        #             straight-line solution exists every sample is rejected and its loop never ends
+        if informed and goal_node is not None and distance(start, target) + distance(target, goal) >= goal_node.cost:
+            continue
+        nearest = argmin(lambda n: distance(n.config, target), tree)
+        grown = safe_path(extend(nearest.config, target), collision)
+        if not grown:
+            continue
+        tip = grown[-1]
+        fresh = OptimalNode(tip, parent=nearest, d=distance(nearest.config, tip), path=grown[:-1], iteration=it)
+        if aim_at_goal and distance(tip, goal) < 1e-6:
+            goal_node = fresh
+            goal_node.set_solution(True)
+        near = [n for n in tree if np.all(distance(n.config, tip) < radius)]
+        tree.append(fresh)
+        for n in near:                                   # better parent for the new node?
+            d = distance(n.config, tip)
+            if n.cost + d < fresh.cost:
+                edge = safe_path(extend(n.config, tip), collision)
+                if edge and distance(tip, edge[-1]) < 1e-6:
+                    fresh.rewire(n, d, edge[:-1], iteration=it)
+        for n in near:                                   # is the new node a better parent for its neighbours?
+            d = distance(tip, n.config)
+            if fresh.cost + d < n.cost:
+                edge = safe_path(extend(tip, n.config), collision)
+                if edge and distance(n.config, edge[-1]) < 1e-6:
+                    n.rewire(fresh, d, edge[:-1], iteration=it)
+    return None if goal_node is None else goal_node.retrace()
 
 
 def rrt_star_force_aware(start, goal, distance, sample, extend, collision, torque_fn, dynam_fn, radius,
