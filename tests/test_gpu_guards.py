@@ -77,3 +77,32 @@ def test_output_guard_bands(n):
     torch.cuda.synchronize()
     assert all(intact(b, 7 * ns, s) for b, _, s in outs) and intact(bk, ns, sk)
     assert 0 <= int(first.item()) <= ns
+
+
+def test_concurrent_host_calls_share_the_default_workspace(eng):
+    """Python threads calling the host-array entry points at once: the shared default workspace is serialised by
+    its lock, device calls on per-thread streams need none.  Every thread must get its own inputs' results."""
+    import threading
+
+    import oracle
+    import torch
+    jobs = [sample_states(30_000 + 1000 * i, seed=50 + i) for i in range(6)]
+    want = [oracle.torque_test_batch("rne", *j) for j in jobs]
+    got = [None] * len(jobs)
+
+    def host_job(i):
+        got[i] = eng.torque_test_batch(*jobs[i], mode="rne")
+
+    def device_job(i):
+        with torch.cuda.stream(torch.cuda.Stream()):
+            dev = [torch.as_tensor(a, device="cuda") for a in jobs[i]]
+            tau, ok = eng.torque_test_batch(*dev, mode="rne")
+            got[i] = (tau.cpu().numpy(), ok.cpu().numpy())
+
+    threads = [threading.Thread(target=host_job if i % 2 == 0 else device_job, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for (tau, ok), (tau_o, ok_o) in zip(got, want):
+        assert np.abs(tau - tau_o).max() < 1e-9 and np.array_equal(ok, ok_o)

@@ -14,6 +14,7 @@ raises.
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Optional
 
 import numpy as np
@@ -81,6 +82,9 @@ class Workspace:
 
     def __init__(self, chunk_states: int = 0):
         self._h = ctypes.c_void_p()
+        # a tcmp_workspace serialises nothing itself: one host call at a time per workspace (the shared default
+        # workspace is what concurrent Python threads would otherwise collide on)
+        self.lock = threading.Lock()
         check(load().tcmp_workspace_create(ctypes.byref(self._h), int(chunk_states)))
 
     @property
@@ -210,8 +214,9 @@ def torque_test_batch(q, qd=None, qdd=None, payload_mass=0.0, mode: str = "rne",
     pma = _as_host(pm, dtype, (n,))
     tau = np.empty((7, n), dtype=_NP[dtype]) if want_tau else None
     mask = np.empty((n,), dtype=np.uint8) if want_mask else None
-    check(lib.tcmp_rne_batch_host(ws.handle, MODE[mode], DTYPE[dtype], n, _nptr(qa), _nptr(qda), _nptr(qdda),
-                                  _nptr(pma), scalar, float(payload_threshold), _nptr(tau), _nptr(mask)))
+    with ws.lock:
+        check(lib.tcmp_rne_batch_host(ws.handle, MODE[mode], DTYPE[dtype], n, _nptr(qa), _nptr(qda), _nptr(qdda),
+                                      _nptr(pma), scalar, float(payload_threshold), _nptr(tau), _nptr(mask)))
     return tau, mask
 
 
@@ -219,9 +224,10 @@ def torque_test_batch_host_into(ws: Workspace, mode, dtype, q, qd, qdd, payload_
                                 payload_threshold, tau_out, mask_out) -> None:
     """Allocation-free host call for benchmarking: every array is a preallocated (pinned) ndarray."""
     n = int(q.shape[1])
-    check(load().tcmp_rne_batch_host(ws.handle, MODE[mode], DTYPE[dtype], n, _nptr(q), _nptr(qd), _nptr(qdd),
-                                     _nptr(payload_mass), float(payload_scalar), float(payload_threshold),
-                                     _nptr(tau_out), _nptr(mask_out)))
+    with ws.lock:
+        check(load().tcmp_rne_batch_host(ws.handle, MODE[mode], DTYPE[dtype], n, _nptr(q), _nptr(qd), _nptr(qdd),
+                                         _nptr(payload_mass), float(payload_scalar), float(payload_threshold),
+                                         _nptr(tau_out), _nptr(mask_out)))
 
 
 def edge_feasibility(qa, qb, n_waypoints: int = 64, payload_mass: float = 0.0, mode: str = "rne",
@@ -246,9 +252,10 @@ def edge_feasibility(qa, qb, n_waypoints: int = 64, payload_mass: float = 0.0, m
     a = _as_host(qa, dtype, (7, n))
     b = _as_host(qb, dtype, (7, n))
     ff = np.empty((n,), dtype=np.int32)
-    check(lib.tcmp_edge_feasibility_host(ws.handle, MODE[mode], DTYPE[dtype], n, int(n_waypoints), _nptr(a),
-                                         _nptr(b), float(payload_mass), float(payload_threshold),
-                                         int(static_only), _nptr(ff)))
+    with ws.lock:
+        check(lib.tcmp_edge_feasibility_host(ws.handle, MODE[mode], DTYPE[dtype], n, int(n_waypoints), _nptr(a),
+                                             _nptr(b), float(payload_mass), float(payload_threshold),
+                                             int(static_only), _nptr(ff)))
     return ff
 
 
@@ -313,8 +320,9 @@ def ik_batch(rot9, trans3, free, want_sols: bool = True, want_status: bool = Tru
     sols = np.empty((n * n_free, 8, 7), dtype=np.float64) if want_sols else None
     counts = np.empty((n * n_free,), dtype=np.int32)
     status = np.empty((n * n_free,), dtype=np.uint8) if want_status else None
-    check(lib.tcmp_ik_batch_host(ws.handle, n, _nptr(r), _nptr(t), _nptr(f), n_free, bcast, _nptr(sols),
-                                 _nptr(counts), _nptr(status)))
+    with ws.lock:
+        check(lib.tcmp_ik_batch_host(ws.handle, n, _nptr(r), _nptr(t), _nptr(f), n_free, bcast, _nptr(sols),
+                                     _nptr(counts), _nptr(status)))
     return sols, counts, status
 
 
