@@ -79,13 +79,14 @@ def test_output_guard_bands(n):
     assert 0 <= int(first.item()) <= ns
 
 
-def test_concurrent_host_calls_share_the_default_workspace(eng):
+def test_concurrent_host_calls_share_the_default_workspace():
     """Python threads calling the host-array entry points at once: the shared default workspace is serialised by
     its lock, device calls on per-thread streams need none.  Every thread must get its own inputs' results."""
     import threading
 
     import oracle
     import torch
+    from torque_constrained_motion_planning_b200 import engine as eng
     jobs = [sample_states(30_000 + 1000 * i, seed=50 + i) for i in range(6)]
     want = [oracle.torque_test_batch("rne", *j) for j in jobs]
     got = [None] * len(jobs)
