@@ -147,6 +147,47 @@ def cpu_baseline_run(n_sample, reps, nthreads=0):
     return n_sample * reps / dt, cores, dt
 
 
+def sample_edges(n, seed):
+    """configs[3] distribution: q_a uniform in the joint limits, q_b = clip(q_a + N(0, 0.5^2))."""
+    rng = np.random.default_rng(seed)
+    qa = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, n))
+    qb = np.clip(qa + rng.normal(0.0, 0.5, size=(7, n)), Q_LO[:, None], Q_HI[:, None])
+    return qa, qb
+
+
+def cpu_baseline_extras(nthreads=0):
+    """CPU arms of the two other workloads, on bounded samples: the UNMODIFIED reference IKFast (oracle/_ref, compiled
+    from the reference's own ikfast_panda_arm.cpp) on 40k poses x 25 free values of configs[2], and the C oracle's
+    edge check on 4k edges x 64 waypoints of configs[3]; OpenMP over every host thread."""
+    import oracle
+    if nthreads == 0:
+        nthreads = len(os.sched_getaffinity(0))
+    out = {}
+    if oracle.have_ref():
+        rng = np.random.default_rng(3)
+        n, n_free = 40_000, 25
+        q = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, n))
+        free = np.empty((n_free, n))
+        free[0] = q[6]
+        free[1:] = rng.uniform(-2.8973, 2.8973, size=(n_free - 1, n))
+        trans, rot = oracle.ref_fk_batch(q)
+        oracle.ref_ik_batch(rot, trans, free, nthreads=nthreads, want_sols=False)      # warm: threads, pages
+        t0 = time.perf_counter()
+        oracle.ref_ik_batch(rot, trans, free, nthreads=nthreads, want_sols=False)
+        dt = time.perf_counter() - t0
+        out["ik"] = {"value": n * n_free / dt, "unit": "solves/s", "cores": nthreads, "kind": "reference",
+                     "sample": "40k poses x 25 free values (1M solves) of configs[2], ComputeIk of the unmodified "
+                               "ikfast_panda_arm.cpp compiled as oracle/_ref, solution counts kept"}
+    qa, qb = sample_edges(4_000, 4)
+    oracle.edge_feasibility("rne", qa[:, :64], qb[:, :64], 64, 5.0, nthreads=nthreads)
+    t0 = time.perf_counter()
+    oracle.edge_feasibility("rne", qa, qb, 64, 5.0, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    out["edges"] = {"value": 4_000 / dt, "unit": "edges/s", "cores": nthreads, "kind": "port",
+                    "sample": "4k edges x 64 min-jerk waypoints of configs[3], rne, 5 kg, C oracle"}
+    return out
+
+
 def python_port_rate(n=300):
     """States/s of ONE core running the NumPy restatement that keeps rne.py's per-call structure (np.block 6x6
     algebra, np.linalg.inv per link): what the reference's own torque test costs on this host."""
@@ -492,6 +533,8 @@ def main():
                                    "python_port_note": "oracle/rne_numpy_port.py: NumPy restatement at rne.py's own "
                                                        "per-call granularity (np.block / np.linalg.inv per link), "
                                                        "300 states on one core"}
+            if world == 1:
+                out["cpu_baseline"]["other_workloads"] = cpu_baseline_extras()
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
