@@ -107,3 +107,56 @@ def test_concurrent_host_calls_share_the_default_workspace():
         t.join()
     for (tau, ok), (tau_o, ok_o) in zip(got, want):
         assert np.abs(tau - tau_o).max() < 1e-9 and np.array_equal(ok, ok_o)
+
+
+def test_entry_points_are_cuda_graph_capturable():
+    """The device entry points only enqueue (no allocation, no synchronisation, parameters by value), so a planner
+    can capture its launch-bound inner loop once and replay it: K1 (with its programmatic-dependent-launch
+    attribute), the static test, the edge kernel and FK are captured into one CUDA graph, the inputs are then
+    overwritten IN PLACE, and each replay must reproduce what direct calls give on the new contents."""
+    import torch
+    from torque_constrained_motion_planning_b200 import engine as eng
+    n, e = 20_000, 512
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+    q, qd, qdd, m = (dev(a) for a in sample_states(n, seed=61))
+    qa, qb = (dev(a) for a in sample_edges(e, seed=62))
+    tau = torch.empty((7, n), dtype=torch.float64, device="cuda")
+    ok = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ok_nov = torch.empty(n, dtype=torch.uint8, device="cuda")
+    lib = eng.load()
+    ff = torch.empty(e, dtype=torch.int32, device="cuda")
+    trans = torch.empty((3, n), dtype=torch.float64, device="cuda")
+    rot = torch.empty((9, n), dtype=torch.float64, device="cuda")
+
+    def enqueue():
+        st = int(torch.cuda.current_stream().cuda_stream)
+        eng.torque_test_batch(q, qd, qdd, m, mode="rne", out_tau=tau, out_mask=ok)
+        eng.torque_test_batch(q, None, None, m, mode="nov", want_tau=False, out_mask=ok_nov)
+        eng.check(lib.tcmp_edge_feasibility(0, 0, e, 64, qa.data_ptr(), qb.data_ptr(), 5.0, 0.01, 0, ff.data_ptr(), st))
+        eng.check(lib.tcmp_fk_batch(n, q.data_ptr(), trans.data_ptr(), rot.data_ptr(), st))
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        enqueue()                                   # warm-up outside capture (module load, occupancy queries)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        enqueue()
+    for seed in (63, 64):
+        nq, nqd, nqdd, nm = (dev(a) for a in sample_states(n, seed=seed))
+        na, nb = (dev(a) for a in sample_edges(e, seed=seed + 10))
+        for dst, src in ((q, nq), (qd, nqd), (qdd, nqdd), (m, nm), (qa, na), (qb, nb)):
+            dst.copy_(src)
+        for t in (tau, trans, rot):
+            t.fill_(float("nan"))
+        ok.fill_(7); ok_nov.fill_(7); ff.fill_(-9)
+        graph.replay()
+        torch.cuda.synchronize()
+        got = [t.clone() for t in (tau, ok, ok_nov, ff, trans, rot)]
+        want_tau, want_ok = eng.torque_test_batch(nq, nqd, nqdd, nm, mode="rne")
+        _, want_nov = eng.torque_test_batch(nq, None, None, nm, mode="nov", want_tau=False)
+        want_ff = eng.edge_feasibility(na, nb, 64, 5.0, mode="rne")
+        want_trans, want_rot = eng.fk_batch(nq)
+        for g, w in zip(got, (want_tau, want_ok, want_nov, want_ff, want_trans, want_rot)):
+            assert torch.equal(g, w)
