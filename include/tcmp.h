@@ -223,6 +223,30 @@ int tcmp_extend_prefix(int mode, int64_t n_edges, const double *q1, const double
                        int32_t *prefix_out, void *stream);
 
 /*
+ * The planner-side entry points with a caller-supplied inertial set: same arguments as the functions of the same
+ * name without the suffix, preceded by the record (host pointer, read during the call; NULL = compiled-in Panda).
+ * Together with tcmp_rne_batch_model they let a whole plan -- tree growth (extend prefix), goal-IK selection, edge
+ * checks, final trajectory check and torque logging -- run on another hand / payload lever / limit set.
+ */
+int tcmp_edge_feasibility_model(const tcmp_model *model, int mode, int dtype, int64_t n_edges, int n_waypoints,
+                                const void *qa, const void *qb, double payload_scalar, double payload_threshold,
+                                int static_only, int32_t *first_fail_out, void *stream);
+int tcmp_traj_feasibility_model(const tcmp_model *model, int mode, int dtype, int n_seg, int samples_per_segment,
+                                const double *coeffs, double payload_scalar, double payload_threshold,
+                                void *q_out, void *qd_out, void *qdd_out, void *tau_out, uint8_t *feasible_out,
+                                int32_t *first_fail_out, void *stream);
+int tcmp_ik_select_model(const tcmp_model *model, int64_t n, const double *rot9, const double *trans3,
+                         const double *free_vals, int n_free, int free_broadcast, const double *q_ref,
+                         int ref_broadcast, const double *q_lo_host, const double *q_hi_host, int mode,
+                         double payload_scalar, double payload_threshold, int use_max_norm, double *best_q,
+                         double *best_cost, int32_t *n_valid, void *stream);
+int tcmp_extend_prefix_model(const tcmp_model *model, int mode, int64_t n_edges, const double *q1, const double *q2,
+                             const double *resolution_host, int n_obs, const tcmp_obstacle *obstacles_host,
+                             const double *q_lo_host, const double *q_hi_host, double payload_radius,
+                             double payload_scalar, double payload_threshold, int32_t *n_steps_out,
+                             int32_t *prefix_out, void *stream);
+
+/*
  * Host-buffer variants: the call a Python/C caller makes with ordinary (ideally pinned) host
  * arrays.  They stage through a caller-created workspace (device buffers + streams), pipeline
  * host->device copies, kernels and device->host copies in chunks, and return after the results

@@ -489,9 +489,10 @@ void oracle_minjerk_trajectory(int L, const double *coeffs, int num_intervals,
  * of the first infeasible waypoint (rrt_star.py:208-210 stops at the first failure),
  * or W when the whole edge is feasible.  qa/qb SoA [7][n_edges].
  */
-void oracle_edge_feasibility(int mode, int64_t n_edges, int W, const double *qa, const double *qb,
-                             double payload_mass, double payload_threshold,
-                             int32_t *first_fail, int nthreads) {
+void oracle_edge_feasibility_model(const oracle_model *mdl, int mode, int64_t n_edges, int W, const double *qa,
+                                   const double *qb, double payload_mass, double payload_threshold,
+                                   int32_t *first_fail, int nthreads) {
+    if (!mdl) mdl = &PANDA;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #pragma omp parallel for schedule(dynamic, 64)
@@ -507,7 +508,7 @@ void oracle_edge_feasibility(int mode, int64_t n_edges, int W, const double *qa,
         for (int w = 0; w < W; w++) {
             double t = oracle_linspace_sample(W, w), x[7], v[7], a[7];
             for (int j = 0; j < 7; j++) minjerk_point(coeffs + j * 6, t, &x[j], &v[j], &a[j]);
-            if (!oracle_torque_test(mode, x, v, a, payload_mass, payload_threshold, 0)) {
+            if (!torque_test_with(mdl, mode, x, v, a, payload_mass, payload_threshold, 0)) {
                 ff = w;
                 break;
             }
@@ -515,13 +516,20 @@ void oracle_edge_feasibility(int mode, int64_t n_edges, int W, const double *qa,
         first_fail[e] = ff;
     }
 }
+void oracle_edge_feasibility(int mode, int64_t n_edges, int W, const double *qa, const double *qb,
+                             double payload_mass, double payload_threshold,
+                             int32_t *first_fail, int nthreads) {
+    oracle_edge_feasibility_model(&PANDA, mode, n_edges, W, qa, qb, payload_mass, payload_threshold, first_fail,
+                                  nthreads);
+}
 
 /* Final-trajectory check (rrt_star.py:203-210): samples of the multi-segment min-jerk
  * through path[L][7]; mask per sample and the first failing index (n_samples if none). */
-void oracle_traj_feasibility(int mode, int L, const double *path, int num_intervals,
-                             double payload_mass, double payload_threshold,
-                             double *tau_out /* [n_samples][7] or NULL */,
-                             uint8_t *mask_out, int32_t *first_fail) {
+void oracle_traj_feasibility_model(const oracle_model *mdl, int mode, int L, const double *path, int num_intervals,
+                                   double payload_mass, double payload_threshold,
+                                   double *tau_out /* [n_samples][7] or NULL */,
+                                   uint8_t *mask_out, int32_t *first_fail) {
+    if (!mdl) mdl = &PANDA;
     const int ns = (L - 1) * num_intervals;
     double coeffs[(L - 1) * 7 * 6];
     oracle_minjerk_coefficients(L, path, coeffs);
@@ -532,13 +540,19 @@ void oracle_traj_feasibility(int mode, int L, const double *path, int num_interv
             double t = oracle_linspace_sample(num_intervals, it), x[7], v[7], a[7], tau[7];
             for (int j = 0; j < 7; j++)
                 minjerk_point(coeffs + ((size_t)seg * 7 + j) * 6, t, &x[j], &v[j], &a[j]);
-            int ok = oracle_torque_test(mode, x, v, a, payload_mass, payload_threshold, tau);
+            int ok = torque_test_with(mdl, mode, x, v, a, payload_mass, payload_threshold, tau);
             if (tau_out)
                 for (int j = 0; j < 7; j++) tau_out[(size_t)row * 7 + j] = tau[j];
             if (mask_out) mask_out[row] = (uint8_t)ok;
             if (!ok && row < ff) ff = row;
         }
     if (first_fail) *first_fail = ff;
+}
+void oracle_traj_feasibility(int mode, int L, const double *path, int num_intervals,
+                             double payload_mass, double payload_threshold,
+                             double *tau_out, uint8_t *mask_out, int32_t *first_fail) {
+    oracle_traj_feasibility_model(&PANDA, mode, L, path, num_intervals, payload_mass, payload_threshold, tau_out,
+                                  mask_out, first_fail);
 }
 
 int oracle_num_threads(void) {

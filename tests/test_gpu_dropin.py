@@ -291,3 +291,34 @@ def test_ikfast_and_franka_front_ends():
     assert conf is not None and not ik_utils.violates_limits(conf)
     t, _ = ik.get_fk_batch(np.array(conf).reshape(7, 1))
     assert np.abs(t[:, 0] - np.array(pose8[0])).max() < 1e-6
+
+
+def test_planner_with_another_inertial_set():
+    """Problem(..., model=...) carries the caller's robot through tree growth, the final trajectory check and the
+    logged torques: every sample of the returned plan passes the OTHER robot's torque test, and the logged torques
+    are the other robot's (rne without payload, utils.py:3376-3378)."""
+    from torque_constrained_motion_planning_b200 import collision, engine, ikfast_panda_arm as ik, ik_utils
+    from torque_constrained_motion_planning_b200 import panda_primitives as pp, utils
+    other = engine.InertialModel.default()
+    other.mass[8] = 1.2                       # hand 0.68 -> 1.2 kg, COM 6 cm below the flange
+    other.com[8] = [0.0, 0.0, 0.06]
+    other.torque_limit[:] = [80, 80, 80, 80, 11, 11, 12]
+    goal_q = [0.7, 0.3, 0.2, -1.9, 0.1, 2.2, 1.0]
+    pos8, rot8 = ik.get_fk(goal_q)
+    c, s_ = math.cos(-math.pi / 4), math.sin(-math.pi / 4)
+    Rt = np.array(rot8) @ np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1.0]])
+    pose = (tuple(np.array(pos8) + Rt @ np.array([0, 0, 0.105])), tuple(ik_utils.quat_from_matrix(Rt)))
+    random.seed(3)
+    np.random.seed(3)
+    problem = utils.Problem(robot=None, fixed=collision.hiro_scene(), payload="coke", payload_mass=1.0,
+                            execution_time=2, torque_test="rne", model=other)
+    plan = pp.planner_fn_force_aware(tuple(Q_HOME), pose, problem, as_arrays=True)
+    assert plan is not None and plan["q"].shape[0] > 100
+    soa = lambda a: np.ascontiguousarray(a.T)
+    _, ok = oracle.torque_test_batch("rne", soa(plan["q"]), soa(plan["qd"]), soa(plan["qdd"]), 1.0, model=other.record)
+    assert ok.all()
+    tau_other, _ = oracle.torque_test_batch("rne", soa(plan["q"]), soa(plan["qd"]), soa(plan["qdd"]), 0.0,
+                                            model=other.record)
+    tau_stock, _ = oracle.torque_test_batch("rne", soa(plan["q"]), soa(plan["qd"]), soa(plan["qdd"]), 0.0)
+    assert np.abs(plan["torques"] - tau_other.T).max() < 1e-9
+    assert np.abs(plan["torques"] - tau_stock.T).max() > 0.5

@@ -497,3 +497,80 @@ def test_default_model_record_equals_compiled_in_kernels(eng):
     bad.mass[0] = float("inf")
     with pytest.raises(eng.TcmpError, match="mass"):
         eng.torque_test_batch(dev(q), dev(qd), dev(qdd), dev(mass), model=bad)
+
+
+# ---- caller-supplied inertial set on the planner-side entry points ---------------------------------------------
+def _other_robot(eng):
+    g = load_golden("model_override.npz")
+    return eng.InertialModel(g["model"]), g["model"]
+
+
+def test_model_edges_and_trajectory_vs_oracle(eng):
+    """tcmp_edge_feasibility_model / tcmp_traj_feasibility_model against the model-parametrised oracle."""
+    model, rec = _other_robot(eng)
+    qa, qb = sample_edges(5_000, seed=71)
+    for mode, W in [("rne", 64), ("nov", 64), ("dyn", 40)]:
+        ff = eng.edge_feasibility(dev(qa), dev(qb), W, 3.0, mode=mode, model=model)
+        ff_o = oracle.edge_feasibility(mode, qa, qb, W, 3.0, model=rec)
+        assert (ff.cpu().numpy() == ff_o).all(), mode
+        assert 0.05 < (ff_o < W).mean() < 0.95
+        assert (ff_o != oracle.edge_feasibility(mode, qa, qb, W, 3.0)).any()       # and it is another robot
+    assert (eng.edge_feasibility(qa[:, :300], qb[:, :300], 64, 3.0, model=model)
+            == oracle.edge_feasibility("rne", qa[:, :300], qb[:, :300], 64, 3.0, model=rec)).all()   # host arrays
+    t = load_golden("traj.npz")
+    coeffs = oracle.minjerk_coefficients(t["points"])
+    for mode in ("rne", "nov", "dyn"):
+        out = eng.traj_feasibility(coeffs, int(t["n_int"]), 2.0, mode=mode, model=model)
+        tau_o, mask_o, ff_o = oracle.traj_feasibility(mode, t["points"], int(t["n_int"]), 2.0, model=rec)
+        assert np.abs(out["tau"].cpu().numpy().T - tau_o).max() < TOL64
+        assert (out["feasible"].cpu().numpy() == mask_o).all() and out["first_fail"] == ff_o
+
+
+def test_model_ik_select_and_extend_prefix(eng):
+    """tcmp_ik_select_model / tcmp_extend_prefix_model: the static torque test inside both uses the caller's robot."""
+    from conftest import Q_HI, Q_LO
+    from torque_constrained_motion_planning_b200 import collision, rrt_star, utils
+    model, rec = _other_robot(eng)
+    rng = np.random.default_rng(72)
+    n, nf = 1500, 5
+    q = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, n))
+    trans, rot = oracle.ref_fk_batch(q)
+    free = np.vstack([q[6:7], rng.uniform(Q_LO[6], Q_HI[6], size=(nf - 1, n))])
+    q_ref = np.clip(q + rng.normal(0, 0.4, size=q.shape), Q_LO[:, None], Q_HI[:, None])
+    sols, counts = oracle.ref_ik_batch(rot, trans, free)
+    best, cost, nv = eng.ik_select(rot, trans, free, q_ref, 3.0, mode="rne", model=model)
+    exp_cost, exp_nv = np.full(n, np.inf), np.zeros(n, dtype=np.int32)
+    cand, owner = [], []
+    for p in range(n):
+        for s in range(p * nf, (p + 1) * nf):
+            for k in range(counts[s]):
+                if np.all(sols[s, k] >= Q_LO) and np.all(sols[s, k] <= Q_HI):
+                    cand.append(sols[s, k]); owner.append(p)
+    cand = np.array(cand)
+    _, ok = oracle.torque_test_batch("rne", np.ascontiguousarray(cand.T), None, None, 3.0, model=rec)
+    _, ok_stock = oracle.torque_test_batch("rne", np.ascontiguousarray(cand.T), None, None, 3.0)
+    assert (ok != ok_stock).any()
+    for c, p, o in zip(cand, owner, ok):
+        if o:
+            exp_nv[p] += 1
+            exp_cost[p] = min(exp_cost[p], np.abs(c - q_ref[:, p]).max())
+    assert np.array_equal(nv, exp_nv)
+    fin = np.isfinite(exp_cost)
+    assert np.array_equal(np.isfinite(cost), fin) and np.abs(cost[fin] - exp_cost[fin]).max() < 1e-9
+    # extend prefix
+    E = 200
+    q1 = rng.uniform(Q_LO, Q_HI, size=(E, 7))
+    q2 = np.clip(q1 + rng.normal(0, 0.8, size=(E, 7)), Q_LO, Q_HI)
+    res = 0.1 * np.ones(7)
+    scene = collision.hiro_scene()
+    col = collision.get_collision_fn(obstacles=scene)
+    ext = utils.get_extend_fn(None, list(range(7)), resolutions=res)
+
+    def tq(qc):
+        return bool(oracle.torque_test_batch("rne", np.asarray(qc, dtype=float).reshape(7, 1), None, None, 3.0,
+                                             model=rec)[1][0])
+    ns, pre = eng.extend_prefix(np.ascontiguousarray(q1.T), np.ascontiguousarray(q2.T), res, scene, 3.0, mode="rne",
+                                model=model)
+    for e in range(E):
+        seq = list(ext(tuple(q1[e]), tuple(q2[e])))
+        assert ns[e] == len(seq) and pre[e] == len(rrt_star.safe_path_force_aware(seq, lambda c: col(c), tq))

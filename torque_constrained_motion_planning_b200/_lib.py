@@ -31,6 +31,11 @@ SIGNATURES = {
     "tcmp_rne_batch": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _vp, _vp]),
     "tcmp_model_default": (_i32, [_vp]),
     "tcmp_rne_batch_model": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _vp, _vp]),
+    "tcmp_edge_feasibility_model": (_i32, [_vp, _i32, _i32, _i64, _i32, _vp, _vp, _f64, _f64, _i32, _vp, _vp]),
+    "tcmp_traj_feasibility_model": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tcmp_ik_select_model": (_i32, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _f64, _f64, _i32, _vp, _vp,
+                              _vp, _vp]),
+    "tcmp_extend_prefix_model": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _f64, _f64, _f64, _vp, _vp, _vp]),
     "tcmp_rne_batch_scatter": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _i32,
                                       ctypes.POINTER(_vp), _i64, _vp]),
     "tcmp_peer_alloc": (_i32, [ctypes.POINTER(_vp), _i64, ctypes.c_char_p]),

@@ -106,12 +106,12 @@ collision_kernel(int64_t n, const double *__restrict__ q, Scene S, uint8_t *__re
     }
 }
 
-template <bool TOOL>
+template <bool TOOL, typename P>
 __global__ void __launch_bounds__(128)
 extend_prefix_kernel(int64_t n_edges, const double *__restrict__ q1, const double *__restrict__ q2, Scene S,
                      double r0, double r1, double r2, double r3, double r4, double r5, double r6, int check_torque,
                      double mass, double payload_threshold, int32_t *__restrict__ n_steps_out,
-                     int32_t *__restrict__ prefix_out) {
+                     int32_t *__restrict__ prefix_out, const __grid_constant__ P prm) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -148,8 +148,8 @@ extend_prefix_kernel(int64_t n_edges, const double *__restrict__ q1, const doubl
             if (!bad && check_torque) {   // torque only for collision-free configurations (rrt_star.py:92-96)
                 double tau[7];
                 const double z[7] = {0, 0, 0, 0, 0, 0, 0};
-                rne_core<double, false, TOOL>(q, z, z, mp_inertial, mp_tool, tau);
-                bad = !within_limits<double>(tau);
+                rne_core<double, false, TOOL, P>(q, z, z, mp_inertial, mp_tool, tau, prm);
+                bad = !limits_ok<double, P>(tau, prm);
             }
             const unsigned fails = __ballot_sync(0xffffffffu, active && bad);
             if (fails) {
@@ -194,26 +194,41 @@ cudaError_t launch_collision_batch(int64_t n, const double *q, int n_obs, const 
     return cudaGetLastError();
 }
 
+template <bool TOOL, typename P>
+static cudaError_t launch_extend_p(int64_t n_edges, const double *q1, const double *q2, const Scene &S, const double *res,
+                                   int check, double mass, double payload_threshold, int32_t *n_steps_out,
+                                   int32_t *prefix_out, const P &prm, cudaStream_t st) {
+    auto kern = extend_prefix_kernel<TOOL, P>;
+    const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, n_edges * 32);
+    kern<<<grid, 128, 0, st>>>(n_edges, q1, q2, S, res[0], res[1], res[2], res[3], res[4], res[5], res[6], check, mass,
+                               payload_threshold, n_steps_out, prefix_out, prm);
+    return cudaGetLastError();
+}
+
+template <bool TOOL>
+static cudaError_t launch_extend_t(int64_t n_edges, const double *q1, const double *q2, const Scene &S, const double *res,
+                                   int check, double mass, double payload_threshold, int32_t *n_steps_out,
+                                   int32_t *prefix_out, const tcmp_model *model, cudaStream_t st) {
+    if (model)
+        return launch_extend_p<TOOL>(n_edges, q1, q2, S, res, check, mass, payload_threshold, n_steps_out, prefix_out,
+                                     params_from_desc<double>(*model), st);
+    return launch_extend_p<TOOL>(n_edges, q1, q2, S, res, check, mass, payload_threshold, n_steps_out, prefix_out,
+                                 ConstParams(), st);
+}
+
 cudaError_t launch_extend_prefix(int mode, int64_t n_edges, const double *q1, const double *q2,
                                  const double *res, int n_obs, const tcmp_obstacle *obs, const double *q_lo,
                                  const double *q_hi, double payload_radius, double mass, double payload_threshold,
-                                 int32_t *n_steps_out, int32_t *prefix_out, cudaStream_t st) {
+                                 int32_t *n_steps_out, int32_t *prefix_out, cudaStream_t st, const tcmp_model *model) {
     Scene S;
     cudaError_t e = make_scene(n_obs, obs, q_lo, q_hi, payload_radius, &S);
     if (e != cudaSuccess) return e;
     const int check = mode != TCMP_MODE_BASE;
-    if (mode == TCMP_MODE_DYN) {
-        const int grid = grid_for(reinterpret_cast<const void *>(extend_prefix_kernel<true>), 128, n_edges * 32);
-        extend_prefix_kernel<true><<<grid, 128, 0, st>>>(n_edges, q1, q2, S, res[0], res[1], res[2], res[3], res[4],
-                                                         res[5], res[6], check, mass, payload_threshold, n_steps_out,
-                                                         prefix_out);
-    } else {
-        const int grid = grid_for(reinterpret_cast<const void *>(extend_prefix_kernel<false>), 128, n_edges * 32);
-        extend_prefix_kernel<false><<<grid, 128, 0, st>>>(n_edges, q1, q2, S, res[0], res[1], res[2], res[3], res[4],
-                                                          res[5], res[6], check, mass, payload_threshold, n_steps_out,
-                                                          prefix_out);
-    }
-    return cudaGetLastError();
+    if (mode == TCMP_MODE_DYN)
+        return launch_extend_t<true>(n_edges, q1, q2, S, res, check, mass, payload_threshold, n_steps_out, prefix_out,
+                                     model, st);
+    return launch_extend_t<false>(n_edges, q1, q2, S, res, check, mass, payload_threshold, n_steps_out, prefix_out,
+                                  model, st);
 }
 
 }  // namespace tcmp

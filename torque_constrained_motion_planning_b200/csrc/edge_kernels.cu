@@ -29,11 +29,12 @@ struct IndexDests {
     int64_t offset;
 };
 
-template <typename T, bool DYN, bool TOOL>
+// P: ConstParams (compiled-in Panda) or RtParams<T> (caller-supplied inertial set, tcmp_*_model entry points).
+template <typename T, bool DYN, bool TOOL, typename P>
 __global__ void __launch_bounds__(128)
 edge_kernel(int64_t n_edges, int W, double interval, double step, const T *__restrict__ qa,
             const T *__restrict__ qb, T mass, T payload_threshold, int32_t *__restrict__ first_fail,
-            IndexDests dests) {
+            IndexDests dests, const __grid_constant__ P prm) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -66,8 +67,8 @@ edge_kernel(int64_t n_edges, int W, double interval, double step, const T *__res
                     as[j] = A[j] * pa;
                 }
             }
-            rne_core<T, DYN, TOOL>(qs, vs, as, mp_inertial, mp_tool, tau);
-            const unsigned fails = __ballot_sync(0xffffffffu, active && !within_limits<T>(tau));
+            rne_core<T, DYN, TOOL, P>(qs, vs, as, mp_inertial, mp_tool, tau, prm);
+            const unsigned fails = __ballot_sync(0xffffffffu, active && !limits_ok<T, P>(tau, prm));
             if (fails) {
                 first = base + __ffs(fails) - 1;
                 break;
@@ -85,11 +86,12 @@ edge_kernel(int64_t n_edges, int W, double interval, double step, const T *__res
     }
 }
 
-template <typename T, bool DYN, bool TOOL>
+template <typename T, bool DYN, bool TOOL, typename P>
 __global__ void __launch_bounds__(128)
 traj_kernel(int n_seg, int S, double interval, double step, const double *__restrict__ coeffs, T mass,
             T payload_threshold, T *__restrict__ q_out, T *__restrict__ qd_out, T *__restrict__ qdd_out,
-            T *__restrict__ tau_out, uint8_t *__restrict__ feasible_out, int32_t *__restrict__ first_fail) {
+            T *__restrict__ tau_out, uint8_t *__restrict__ feasible_out, int32_t *__restrict__ first_fail,
+            const __grid_constant__ P prm) {
     const int64_t n = (int64_t)n_seg * S;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const T mp_inertial = TOOL ? T(0) : (mass > payload_threshold ? mass : T(0));
@@ -106,8 +108,8 @@ traj_kernel(int n_seg, int S, double interval, double step, const double *__rest
             vs[j] = c1 + t * (T(2) * c2 + t * (T(3) * c3 + t * (T(4) * c4 + t * (T(5) * c5))));  // :218
             as[j] = T(2) * c2 + t * (T(6) * c3 + t * (T(12) * c4 + t * (T(20) * c5)));           // :220
         }
-        rne_core<T, DYN, TOOL>(qs, vs, as, mp_inertial, mp_tool, tau);
-        const bool ok = within_limits<T>(tau);
+        rne_core<T, DYN, TOOL, P>(qs, vs, as, mp_inertial, mp_tool, tau, prm);
+        const bool ok = limits_ok<T, P>(tau, prm);
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
             if (q_out) q_out[j * n + i] = qs[j];
@@ -125,40 +127,50 @@ static void linspace_params(int n, double *interval, double *step) {
     *step = n > 1 ? (1.0 - *interval) / (n - 1) : 0.0;
 }
 
-template <typename T, bool DYN, bool TOOL>
-static cudaError_t launch_edge_t(int64_t n_edges, int W, const void *qa, const void *qb, double ps, double pt,
-                                 int32_t *ff, const IndexDests &dests, cudaStream_t st) {
+template <typename T, bool DYN, bool TOOL, typename P>
+static cudaError_t launch_edge_p(int64_t n_edges, int W, const void *qa, const void *qb, double ps, double pt,
+                                 int32_t *ff, const IndexDests &dests, const P &prm, cudaStream_t st) {
     double interval, step;
     linspace_params(W, &interval, &step);
-    auto kern = edge_kernel<T, DYN, TOOL>;
+    auto kern = edge_kernel<T, DYN, TOOL, P>;
     const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, n_edges * 32, kEdgeWaves);
-    kern<<<grid, 128, 0, st>>>(n_edges, W, interval, step, (const T *)qa, (const T *)qb, (T)ps, (T)pt, ff, dests);
+    kern<<<grid, 128, 0, st>>>(n_edges, W, interval, step, (const T *)qa, (const T *)qb, (T)ps, (T)pt, ff, dests, prm);
     return cudaGetLastError();
+}
+
+template <typename T, bool DYN, bool TOOL>
+static cudaError_t launch_edge_t(int64_t n_edges, int W, const void *qa, const void *qb, double ps, double pt,
+                                 int32_t *ff, const IndexDests &dests, const tcmp_model *model, cudaStream_t st) {
+    if (model)
+        return launch_edge_p<T, DYN, TOOL>(n_edges, W, qa, qb, ps, pt, ff, dests, params_from_desc<T>(*model), st);
+    return launch_edge_p<T, DYN, TOOL>(n_edges, W, qa, qb, ps, pt, ff, dests, ConstParams(), st);
 }
 
 template <typename T>
 static cudaError_t launch_edge_typed(int mode, int64_t n_edges, int W, const void *qa, const void *qb,
                                      double ps, double pt, int static_only, int32_t *ff, const IndexDests &dests,
-                                     cudaStream_t st) {
+                                     const tcmp_model *model, cudaStream_t st) {
     const bool dynamic = (mode != TCMP_MODE_NOV) && !static_only;
     const bool tool = (mode == TCMP_MODE_DYN);
     if (dynamic) {
-        if (tool) return launch_edge_t<T, true, true>(n_edges, W, qa, qb, ps, pt, ff, dests, st);
-        return launch_edge_t<T, true, false>(n_edges, W, qa, qb, ps, pt, ff, dests, st);
+        if (tool) return launch_edge_t<T, true, true>(n_edges, W, qa, qb, ps, pt, ff, dests, model, st);
+        return launch_edge_t<T, true, false>(n_edges, W, qa, qb, ps, pt, ff, dests, model, st);
     }
-    if (tool) return launch_edge_t<T, false, true>(n_edges, W, qa, qb, ps, pt, ff, dests, st);
-    return launch_edge_t<T, false, false>(n_edges, W, qa, qb, ps, pt, ff, dests, st);
+    if (tool) return launch_edge_t<T, false, true>(n_edges, W, qa, qb, ps, pt, ff, dests, model, st);
+    return launch_edge_t<T, false, false>(n_edges, W, qa, qb, ps, pt, ff, dests, model, st);
 }
 
 cudaError_t launch_edge_feasibility(int mode, int dtype, int64_t n_edges, int W, const void *qa, const void *qb,
-                                    double ps, double pt, int static_only, int32_t *ff, cudaStream_t st) {
+                                    double ps, double pt, int static_only, int32_t *ff, cudaStream_t st,
+                                    const tcmp_model *model) {
     IndexDests none;
     none.n = 0;
     none.offset = 0;
     for (int i = 0; i < TCMP_MAX_PEERS; ++i) none.p[i] = nullptr;
     if (mode == TCMP_MODE_BASE) return launch_fill<int32_t>(n_edges, ff, W, st);
-    if (dtype == TCMP_F64) return launch_edge_typed<double>(mode, n_edges, W, qa, qb, ps, pt, static_only, ff, none, st);
-    return launch_edge_typed<float>(mode, n_edges, W, qa, qb, ps, pt, static_only, ff, none, st);
+    if (dtype == TCMP_F64)
+        return launch_edge_typed<double>(mode, n_edges, W, qa, qb, ps, pt, static_only, ff, none, model, st);
+    return launch_edge_typed<float>(mode, n_edges, W, qa, qb, ps, pt, static_only, ff, none, model, st);
 }
 
 cudaError_t launch_edge_feasibility_scatter(int mode, int64_t n_edges, int W, const void *qa, const void *qb,
@@ -173,38 +185,51 @@ cudaError_t launch_edge_feasibility_scatter(int mode, int64_t n_edges, int W, co
         for (int i = 0; i < n_dest && e == cudaSuccess; ++i) e = launch_fill<int32_t>(n_edges, d.p[i] + dest_offset, W, st);
         return e;
     }
-    return launch_edge_typed<double>(mode, n_edges, W, qa, qb, ps, pt, static_only, nullptr, d, st);
+    return launch_edge_typed<double>(mode, n_edges, W, qa, qb, ps, pt, static_only, nullptr, d, nullptr, st);
+}
+
+template <typename T, bool DYN, bool TOOL, typename P>
+static cudaError_t launch_traj_p(int n_seg, int S, const double *coeffs, double ps, double pt, void *q, void *qd,
+                                 void *qdd, void *tau, uint8_t *mask, int32_t *ff, const P &prm, cudaStream_t st) {
+    double interval, step;
+    linspace_params(S, &interval, &step);
+    auto kern = traj_kernel<T, DYN, TOOL, P>;
+    const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, (int64_t)n_seg * S);
+    kern<<<grid, 128, 0, st>>>(n_seg, S, interval, step, coeffs, (T)ps, (T)pt, (T *)q, (T *)qd, (T *)qdd,
+                               (T *)tau, mask, ff, prm);
+    return cudaGetLastError();
 }
 
 template <typename T, bool DYN, bool TOOL>
 static cudaError_t launch_traj_t(int n_seg, int S, const double *coeffs, double ps, double pt, void *q, void *qd,
-                                 void *qdd, void *tau, uint8_t *mask, int32_t *ff, cudaStream_t st) {
-    double interval, step;
-    linspace_params(S, &interval, &step);
-    auto kern = traj_kernel<T, DYN, TOOL>;
-    const int grid = grid_for(reinterpret_cast<const void *>(kern), 128, (int64_t)n_seg * S);
-    kern<<<grid, 128, 0, st>>>(n_seg, S, interval, step, coeffs, (T)ps, (T)pt, (T *)q, (T *)qd, (T *)qdd,
-                               (T *)tau, mask, ff);
-    return cudaGetLastError();
+                                 void *qdd, void *tau, uint8_t *mask, int32_t *ff, const tcmp_model *model,
+                                 cudaStream_t st) {
+    if (model)
+        return launch_traj_p<T, DYN, TOOL>(n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, mask, ff,
+                                           params_from_desc<T>(*model), st);
+    return launch_traj_p<T, DYN, TOOL>(n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, mask, ff, ConstParams(), st);
 }
 
 template <typename T>
 static cudaError_t launch_traj_typed(int mode, int n_seg, int S, const double *coeffs, double ps, double pt,
                                      void *q, void *qd, void *qdd, void *tau, uint8_t *mask, int32_t *ff,
-                                     cudaStream_t st) {
-    if (mode == TCMP_MODE_NOV) return launch_traj_t<T, false, false>(n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, mask, ff, st);
-    if (mode == TCMP_MODE_DYN) return launch_traj_t<T, true, true>(n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, mask, ff, st);
-    return launch_traj_t<T, true, false>(n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, mask, ff, st);
+                                     const tcmp_model *model, cudaStream_t st) {
+    if (mode == TCMP_MODE_NOV)
+        return launch_traj_t<T, false, false>(n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, mask, ff, model, st);
+    if (mode == TCMP_MODE_DYN)
+        return launch_traj_t<T, true, true>(n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, mask, ff, model, st);
+    return launch_traj_t<T, true, false>(n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, mask, ff, model, st);
 }
 
 cudaError_t launch_traj_feasibility(int mode, int dtype, int n_seg, int S, const double *coeffs, double ps,
                                     double pt, void *q, void *qd, void *qdd, void *tau, uint8_t *mask,
-                                    int32_t *ff, cudaStream_t st) {
+                                    int32_t *ff, cudaStream_t st, const tcmp_model *model) {
     if (mode == TCMP_MODE_BASE) {  // constant-true test: only the mask is defined
         return mask ? launch_fill<uint8_t>((int64_t)n_seg * S, mask, 1, st) : cudaSuccess;
     }
-    if (dtype == TCMP_F64) return launch_traj_typed<double>(mode, n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, mask, ff, st);
-    return launch_traj_typed<float>(mode, n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, mask, ff, st);
+    if (dtype == TCMP_F64)
+        return launch_traj_typed<double>(mode, n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, mask, ff, model, st);
+    return launch_traj_typed<float>(mode, n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, mask, ff, model, st);
 }
 
 }  // namespace tcmp

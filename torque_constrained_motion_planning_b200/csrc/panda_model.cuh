@@ -525,4 +525,9 @@ template <typename T> TCMP_FN bool within_limits(const T (&tau)[7], const RtPara
     return ok;
 }
 
+template <typename T, typename P> TCMP_FN bool limits_ok(const T (&tau)[7], const P &p) {
+    if constexpr (kIsConst<P>) return within_limits<T>(tau);
+    else return within_limits<T>(tau, p);
+}
+
 }  // namespace tcmp

@@ -29,13 +29,13 @@ constexpr int kSelWarps = 2;            // warps per CTA
 constexpr int kSelCap = 256;            // 32 lanes x 8 solutions: a round can never overflow the list
 constexpr int kSelRow = 9;              // q[7], cost, key (as double) -- odd stride, conflict-free 64-bit rows
 
-template <bool TOOL>
+template <bool TOOL, typename P>
 __global__ void __launch_bounds__(kSelWarps * 32)
 ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__restrict__ rot9,
                  const double *__restrict__ trans3, const double *__restrict__ free_vals,
                  const double *__restrict__ q_ref, int ref_broadcast, JointLimits lim, int check_torque,
                  double mass, double payload_threshold, int use_max_norm, double *__restrict__ best_q,
-                 double *__restrict__ best_cost, int32_t *__restrict__ n_valid) {
+                 double *__restrict__ best_cost, int32_t *__restrict__ n_valid, const __grid_constant__ P prm) {
     __shared__ double cand_all[kSelWarps][kSelCap * kSelRow];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double *cand = cand_all[wib];
@@ -106,8 +106,8 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
                 if (check_torque) {
                     double tau[7];
                     const double z[7] = {0, 0, 0, 0, 0, 0, 0};
-                    rne_core<double, false, TOOL>(q, z, z, mp_inertial, mp_tool, tau);
-                    ok = within_limits<double>(tau);
+                    rne_core<double, false, TOOL, P>(q, z, z, mp_inertial, mp_tool, tau, prm);
+                    ok = limits_ok<double, P>(tau, prm);
                 }
                 if (ok) {
                     ++valid;
@@ -143,29 +143,49 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
     }
 }
 
+template <bool TOOL, typename P>
+static cudaError_t launch_select_p(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
+                                   int n_free, int free_broadcast, const double *q_ref, int ref_broadcast,
+                                   const JointLimits &lim, int check, double mass, double payload_threshold,
+                                   int use_max_norm, double *best_q, double *best_cost, int32_t *n_valid, const P &prm,
+                                   cudaStream_t st) {
+    auto kern = ik_select_kernel<TOOL, P>;
+    const int grid = grid_for(reinterpret_cast<const void *>(kern), kSelWarps * 32, n * 32, kSelWaves);
+    kern<<<grid, kSelWarps * 32, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref, ref_broadcast, lim,
+                                          check, mass, payload_threshold, use_max_norm, best_q, best_cost, n_valid, prm);
+    return cudaGetLastError();
+}
+
+template <bool TOOL>
+static cudaError_t launch_select_t(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
+                                   int n_free, int free_broadcast, const double *q_ref, int ref_broadcast,
+                                   const JointLimits &lim, int check, double mass, double payload_threshold,
+                                   int use_max_norm, double *best_q, double *best_cost, int32_t *n_valid,
+                                   const tcmp_model *model, cudaStream_t st) {
+    if (model)
+        return launch_select_p<TOOL>(n, rot9, trans3, free_vals, n_free, free_broadcast, q_ref, ref_broadcast, lim,
+                                     check, mass, payload_threshold, use_max_norm, best_q, best_cost, n_valid,
+                                     params_from_desc<double>(*model), st);
+    return launch_select_p<TOOL>(n, rot9, trans3, free_vals, n_free, free_broadcast, q_ref, ref_broadcast, lim, check,
+                                 mass, payload_threshold, use_max_norm, best_q, best_cost, n_valid, ConstParams(), st);
+}
+
 cudaError_t launch_ik_select(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
                              int n_free, int free_broadcast, const double *q_ref, int ref_broadcast,
                              const double *q_lo, const double *q_hi, int mode, double mass,
                              double payload_threshold, int use_max_norm, double *best_q, double *best_cost,
-                             int32_t *n_valid, cudaStream_t st) {
+                             int32_t *n_valid, cudaStream_t st, const tcmp_model *model) {
     JointLimits lim;
     for (int j = 0; j < 7; ++j) {
         lim.lo[j] = q_lo[j];
         lim.hi[j] = q_hi[j];
     }
     const int check = mode != TCMP_MODE_BASE;
-    if (mode == TCMP_MODE_DYN) {
-        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<true>), kSelWarps * 32, n * 32, kSelWaves);
-        ik_select_kernel<true><<<grid, kSelWarps * 32, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref,
-                                                     ref_broadcast, lim, check, mass, payload_threshold, use_max_norm,
-                                                     best_q, best_cost, n_valid);
-    } else {
-        const int grid = grid_for(reinterpret_cast<const void *>(ik_select_kernel<false>), kSelWarps * 32, n * 32, kSelWaves);
-        ik_select_kernel<false><<<grid, kSelWarps * 32, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref,
-                                                      ref_broadcast, lim, check, mass, payload_threshold, use_max_norm,
-                                                      best_q, best_cost, n_valid);
-    }
-    return cudaGetLastError();
+    if (mode == TCMP_MODE_DYN)
+        return launch_select_t<true>(n, rot9, trans3, free_vals, n_free, free_broadcast, q_ref, ref_broadcast, lim,
+                                     check, mass, payload_threshold, use_max_norm, best_q, best_cost, n_valid, model, st);
+    return launch_select_t<false>(n, rot9, trans3, free_vals, n_free, free_broadcast, q_ref, ref_broadcast, lim, check,
+                                  mass, payload_threshold, use_max_norm, best_q, best_cost, n_valid, model, st);
 }
 
 }  // namespace tcmp

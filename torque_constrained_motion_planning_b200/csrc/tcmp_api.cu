@@ -173,6 +173,12 @@ int tcmp_rne_batch(int mode, int dtype, int64_t n, const void *q, const void *qd
     return TCMP_OK;
 }
 
+static int check_model(const tcmp_model *model) {
+    if (!model) return TCMP_OK;
+    if (const char *why = model_desc_problem(*model)) return fail(TCMP_ERR_INVALID_ARG, "tcmp_model: %s", why);
+    return TCMP_OK;
+}
+
 int tcmp_model_default(tcmp_model *out) {
     if (!out) return fail(TCMP_ERR_INVALID_ARG, "model is NULL");
     default_model_desc(out);
@@ -186,7 +192,7 @@ int tcmp_rne_batch_model(const tcmp_model *model, int mode, int dtype, int64_t n
         return tcmp_rne_batch(mode, dtype, n, q, qd, qdd, payload_mass, payload_scalar, payload_threshold, tau_out,
                               feasible_out, stream);
     if (int rc = check_common(mode, dtype, n)) return rc;
-    if (const char *why = model_desc_problem(*model)) return fail(TCMP_ERR_INVALID_ARG, "tcmp_model: %s", why);
+    if (int rc = check_model(model)) return rc;
     if (n == 0) return TCMP_OK;
     if (!q) return fail(TCMP_ERR_INVALID_ARG, "q is NULL");
     if (!tau_out && !feasible_out) return fail(TCMP_ERR_INVALID_ARG, "both outputs are NULL");
@@ -245,16 +251,24 @@ int tcmp_peer_close(void *peer_ptr) {
     return TCMP_OK;
 }
 
-int tcmp_edge_feasibility(int mode, int dtype, int64_t n_edges, int n_waypoints, const void *qa, const void *qb,
-                          double payload_scalar, double payload_threshold, int static_only,
-                          int32_t *first_fail_out, void *stream) {
+int tcmp_edge_feasibility_model(const tcmp_model *model, int mode, int dtype, int64_t n_edges, int n_waypoints,
+                                const void *qa, const void *qb, double payload_scalar, double payload_threshold,
+                                int static_only, int32_t *first_fail_out, void *stream) {
     if (int rc = check_common(mode, dtype, n_edges)) return rc;
+    if (int rc = check_model(model)) return rc;
     if (n_waypoints < 1) return fail(TCMP_ERR_INVALID_ARG, "n_waypoints must be >= 1");
     if (n_edges == 0) return TCMP_OK;
     if (!qa || !qb || !first_fail_out) return fail(TCMP_ERR_INVALID_ARG, "NULL edge buffer");
     TCMP_CUDA(launch_edge_feasibility(mode, dtype, n_edges, n_waypoints, qa, qb, payload_scalar, payload_threshold,
-                                      static_only, first_fail_out, (cudaStream_t)stream));
+                                      static_only, first_fail_out, (cudaStream_t)stream, model));
     return TCMP_OK;
+}
+
+int tcmp_edge_feasibility(int mode, int dtype, int64_t n_edges, int n_waypoints, const void *qa, const void *qb,
+                          double payload_scalar, double payload_threshold, int static_only,
+                          int32_t *first_fail_out, void *stream) {
+    return tcmp_edge_feasibility_model(nullptr, mode, dtype, n_edges, n_waypoints, qa, qb, payload_scalar,
+                                       payload_threshold, static_only, first_fail_out, stream);
 }
 
 int tcmp_edge_feasibility_scatter(int mode, int64_t n_edges, int n_waypoints, const void *qa, const void *qb,
@@ -276,13 +290,23 @@ int tcmp_edge_feasibility_scatter(int mode, int64_t n_edges, int n_waypoints, co
 int tcmp_traj_feasibility(int mode, int dtype, int n_seg, int samples_per_segment, const double *coeffs,
                           double payload_scalar, double payload_threshold, void *q_out, void *qd_out, void *qdd_out,
                           void *tau_out, uint8_t *feasible_out, int32_t *first_fail_out, void *stream) {
+    return tcmp_traj_feasibility_model(nullptr, mode, dtype, n_seg, samples_per_segment, coeffs, payload_scalar,
+                                       payload_threshold, q_out, qd_out, qdd_out, tau_out, feasible_out,
+                                       first_fail_out, stream);
+}
+
+int tcmp_traj_feasibility_model(const tcmp_model *model, int mode, int dtype, int n_seg, int samples_per_segment,
+                                const double *coeffs, double payload_scalar, double payload_threshold, void *q_out,
+                                void *qd_out, void *qdd_out, void *tau_out, uint8_t *feasible_out,
+                                int32_t *first_fail_out, void *stream) {
     if (int rc = check_common(mode, dtype, n_seg)) return rc;
+    if (int rc = check_model(model)) return rc;
     if (samples_per_segment < 1) return fail(TCMP_ERR_INVALID_ARG, "samples_per_segment must be >= 1");
     if (n_seg == 0) return TCMP_OK;
     if (!coeffs) return fail(TCMP_ERR_INVALID_ARG, "coeffs is NULL");
     TCMP_CUDA(launch_traj_feasibility(mode, dtype, n_seg, samples_per_segment, coeffs, payload_scalar,
                                       payload_threshold, q_out, qd_out, qdd_out, tau_out, feasible_out,
-                                      first_fail_out, (cudaStream_t)stream));
+                                      first_fail_out, (cudaStream_t)stream, model));
     return TCMP_OK;
 }
 
@@ -300,6 +324,17 @@ int tcmp_ik_select(int64_t n, const double *rot9, const double *trans3, const do
                    int free_broadcast, const double *q_ref, int ref_broadcast, const double *q_lo_host,
                    const double *q_hi_host, int mode, double payload_scalar, double payload_threshold, int use_max_norm,
                    double *best_q, double *best_cost, int32_t *n_valid, void *stream) {
+    return tcmp_ik_select_model(nullptr, n, rot9, trans3, free_vals, n_free, free_broadcast, q_ref, ref_broadcast,
+                                q_lo_host, q_hi_host, mode, payload_scalar, payload_threshold, use_max_norm, best_q,
+                                best_cost, n_valid, stream);
+}
+
+int tcmp_ik_select_model(const tcmp_model *model, int64_t n, const double *rot9, const double *trans3,
+                         const double *free_vals, int n_free, int free_broadcast, const double *q_ref,
+                         int ref_broadcast, const double *q_lo_host, const double *q_hi_host, int mode,
+                         double payload_scalar, double payload_threshold, int use_max_norm, double *best_q,
+                         double *best_cost, int32_t *n_valid, void *stream) {
+    if (int rc = check_model(model)) return rc;
     if (n < 0 || n_free < 1) return fail(TCMP_ERR_INVALID_ARG, "bad n / n_free");
     if (mode < TCMP_MODE_RNE || mode > TCMP_MODE_BASE) return fail(TCMP_ERR_INVALID_ARG, "bad mode %d", mode);
     if (n == 0) return TCMP_OK;
@@ -307,7 +342,7 @@ int tcmp_ik_select(int64_t n, const double *rot9, const double *trans3, const do
         return fail(TCMP_ERR_INVALID_ARG, "NULL IK-select buffer");
     TCMP_CUDA(launch_ik_select(n, rot9, trans3, free_vals, n_free, free_broadcast, q_ref, ref_broadcast, q_lo_host,
                                q_hi_host, mode, payload_scalar, payload_threshold, use_max_norm, best_q, best_cost,
-                               n_valid, (cudaStream_t)stream));
+                               n_valid, (cudaStream_t)stream, model));
     return TCMP_OK;
 }
 
@@ -328,7 +363,18 @@ int tcmp_extend_prefix(int mode, int64_t n_edges, const double *q1, const double
                        int n_obs, const tcmp_obstacle *obstacles_host, const double *q_lo_host, const double *q_hi_host,
                        double payload_radius, double payload_scalar, double payload_threshold, int32_t *n_steps_out,
                        int32_t *prefix_out, void *stream) {
+    return tcmp_extend_prefix_model(nullptr, mode, n_edges, q1, q2, resolution_host, n_obs, obstacles_host, q_lo_host,
+                                    q_hi_host, payload_radius, payload_scalar, payload_threshold, n_steps_out,
+                                    prefix_out, stream);
+}
+
+int tcmp_extend_prefix_model(const tcmp_model *model, int mode, int64_t n_edges, const double *q1, const double *q2,
+                             const double *resolution_host, int n_obs, const tcmp_obstacle *obstacles_host,
+                             const double *q_lo_host, const double *q_hi_host, double payload_radius,
+                             double payload_scalar, double payload_threshold, int32_t *n_steps_out,
+                             int32_t *prefix_out, void *stream) {
     if (int rc = check_common(mode, TCMP_F64, n_edges)) return rc;
+    if (int rc = check_model(model)) return rc;
     if (n_obs < 0 || n_obs > TCMP_MAX_OBSTACLES) return fail(TCMP_ERR_UNSUPPORTED, "0..%d obstacles", TCMP_MAX_OBSTACLES);
     if (n_edges == 0) return TCMP_OK;
     if (!q1 || !q2 || !resolution_host || !q_lo_host || !q_hi_host || !n_steps_out || !prefix_out ||
@@ -338,7 +384,7 @@ int tcmp_extend_prefix(int mode, int64_t n_edges, const double *q1, const double
         if (!(resolution_host[j] > 0)) return fail(TCMP_ERR_INVALID_ARG, "resolution[%d] must be > 0", j);
     TCMP_CUDA(launch_extend_prefix(mode, n_edges, q1, q2, resolution_host, n_obs, obstacles_host, q_lo_host, q_hi_host,
                                    payload_radius, payload_scalar, payload_threshold, n_steps_out, prefix_out,
-                                   (cudaStream_t)stream));
+                                   (cudaStream_t)stream, model));
     return TCMP_OK;
 }
 

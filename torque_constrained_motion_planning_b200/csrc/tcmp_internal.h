@@ -50,7 +50,8 @@ cudaError_t launch_rne_batch_scatter(int mode, int dtype, int64_t n, const void 
 
 cudaError_t launch_edge_feasibility(int mode, int dtype, int64_t n_edges, int n_waypoints, const void *qa,
                                     const void *qb, double payload_scalar, double payload_threshold,
-                                    int static_only, int32_t *first_fail_out, cudaStream_t st);
+                                    int static_only, int32_t *first_fail_out, cudaStream_t st,
+                                    const tcmp_model *model = nullptr);
 
 cudaError_t launch_edge_feasibility_scatter(int mode, int64_t n_edges, int n_waypoints, const void *qa, const void *qb,
                                             double payload_scalar, double payload_threshold, int static_only,
@@ -59,7 +60,8 @@ cudaError_t launch_edge_feasibility_scatter(int mode, int64_t n_edges, int n_way
 cudaError_t launch_traj_feasibility(int mode, int dtype, int n_seg, int samples_per_segment,
                                     const double *coeffs, double payload_scalar, double payload_threshold,
                                     void *q_out, void *qd_out, void *qdd_out, void *tau_out,
-                                    uint8_t *feasible_out, int32_t *first_fail_out, cudaStream_t st);
+                                    uint8_t *feasible_out, int32_t *first_fail_out, cudaStream_t st,
+                                    const tcmp_model *model = nullptr);
 
 cudaError_t launch_ik_batch(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
                             int n_free, int free_broadcast, double *sols_out, int32_t *count_out,
@@ -69,7 +71,7 @@ cudaError_t launch_ik_select(int64_t n, const double *rot9, const double *trans3
                              int n_free, int free_broadcast, const double *q_ref, int ref_broadcast,
                              const double *q_lo, const double *q_hi, int mode, double mass,
                              double payload_threshold, int use_max_norm, double *best_q, double *best_cost,
-                             int32_t *n_valid, cudaStream_t st);
+                             int32_t *n_valid, cudaStream_t st, const tcmp_model *model = nullptr);
 
 cudaError_t launch_fk_batch(int64_t n, const double *q, double *trans3, double *rot9, cudaStream_t st);
 
@@ -80,7 +82,8 @@ cudaError_t launch_collision_batch(int64_t n, const double *q, int n_obs, const 
 cudaError_t launch_extend_prefix(int mode, int64_t n_edges, const double *q1, const double *q2,
                                  const double *res, int n_obs, const tcmp_obstacle *obs, const double *q_lo,
                                  const double *q_hi, double payload_radius, double mass, double payload_threshold,
-                                 int32_t *n_steps_out, int32_t *prefix_out, cudaStream_t st);
+                                 int32_t *n_steps_out, int32_t *prefix_out, cudaStream_t st,
+                                 const tcmp_model *model = nullptr);
 
 cudaError_t launch_fp64_peak(int iters, double *sink, int *grid_out, int *block_out, cudaStream_t st);
 

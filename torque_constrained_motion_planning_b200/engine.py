@@ -162,6 +162,11 @@ class InertialModel:
         self.record[91] = v
 
 
+def _mptr(model) -> Optional[int]:
+    """Host pointer of an InertialModel's record for the tcmp_*_model entry points (None -> NULL = stock Panda)."""
+    return None if model is None else int(model.record.ctypes.data)
+
+
 def torque_test_batch(q, qd=None, qdd=None, payload_mass=0.0, mode: str = "rne", dtype: str = "f64",
                       payload_threshold: float = PAYLOAD_THRESHOLD_TEST, want_tau: bool = True,
                       want_mask: bool = True, workspace: Optional[Workspace] = None, out_tau=None, out_mask=None,
@@ -232,11 +237,19 @@ def torque_test_batch_host_into(ws: Workspace, mode, dtype, q, qd, qdd, payload_
 
 def edge_feasibility(qa, qb, n_waypoints: int = 64, payload_mass: float = 0.0, mode: str = "rne",
                      dtype: str = "f64", payload_threshold: float = PAYLOAD_THRESHOLD_TEST,
-                     static_only: bool = False, workspace: Optional[Workspace] = None):
+                     static_only: bool = False, workspace: Optional[Workspace] = None,
+                     model: Optional[InertialModel] = None):
     """RRT* edge check (tcmp_edge_feasibility): first infeasible min-jerk waypoint per edge
-    (== n_waypoints when the edge is feasible).  qa/qb ``[7][n_edges]``."""
+    (== n_waypoints when the edge is feasible).  qa/qb ``[7][n_edges]``.  ``model``: another inertial set
+    (tcmp_edge_feasibility_model; host arrays are then staged through torch)."""
     lib = load()
     n = int(qa.shape[1])
+    if model is not None and not _is_cuda_tensor(qa):
+        torch = _torch()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        up = lambda x: torch.as_tensor(_as_host(x, dtype, (7, n)), device=dev)
+        return edge_feasibility(up(qa), up(qb), n_waypoints, payload_mass, mode, dtype, payload_threshold,
+                                static_only, model=model).cpu().numpy()
     if _is_cuda_tensor(qa):
         torch = _torch()
         dev = qa.device
@@ -244,9 +257,9 @@ def edge_feasibility(qa, qb, n_waypoints: int = 64, payload_mass: float = 0.0, m
             a = _as_dev(qa, dtype, (7, n), dev)
             b = _as_dev(qb, dtype, (7, n), dev)
             ff = torch.empty((n,), dtype=torch.int32, device=dev)
-            check(lib.tcmp_edge_feasibility(MODE[mode], DTYPE[dtype], n, int(n_waypoints), _ptr(a), _ptr(b),
-                                            float(payload_mass), float(payload_threshold), int(static_only),
-                                            _ptr(ff), _stream_ptr()))
+            check(lib.tcmp_edge_feasibility_model(_mptr(model), MODE[mode], DTYPE[dtype], n, int(n_waypoints), _ptr(a),
+                                                  _ptr(b), float(payload_mass), float(payload_threshold),
+                                                  int(static_only), _ptr(ff), _stream_ptr()))
         return ff
     ws = workspace or default_workspace()
     a = _as_host(qa, dtype, (7, n))
@@ -261,8 +274,9 @@ def edge_feasibility(qa, qb, n_waypoints: int = 64, payload_mass: float = 0.0, m
 
 def traj_feasibility(coeffs, samples_per_segment: int, payload_mass: float = 0.0, mode: str = "rne",
                      dtype: str = "f64", payload_threshold: float = PAYLOAD_THRESHOLD_TEST,
-                     want_samples: bool = True, want_tau: bool = True, device=None):
-    """Final-trajectory check (tcmp_traj_feasibility) on min-jerk coefficients ``[n_seg][7][6]``.
+                     want_samples: bool = True, want_tau: bool = True, device=None,
+                     model: Optional[InertialModel] = None):
+    """Final-trajectory check (tcmp_traj_feasibility[_model]) on min-jerk coefficients ``[n_seg][7][6]``.
     Returns dict(q, qd, qdd, tau  [7][n] tensors or None, feasible uint8 [n], first_fail int)."""
     torch = _torch()
     lib = load()
@@ -283,9 +297,9 @@ def traj_feasibility(coeffs, samples_per_segment: int, payload_mass: float = 0.0
         tau = mk() if want_tau else None
         mask = torch.empty((n,), dtype=torch.uint8, device=dev)
         ff = torch.full((1,), n, dtype=torch.int32, device=dev)
-        check(lib.tcmp_traj_feasibility(MODE[mode], DTYPE[dtype], n_seg, S, _ptr(ct), float(payload_mass),
-                                        float(payload_threshold), _ptr(q), _ptr(qd), _ptr(qdd), _ptr(tau),
-                                        _ptr(mask), _ptr(ff), _stream_ptr()))
+        check(lib.tcmp_traj_feasibility_model(_mptr(model), MODE[mode], DTYPE[dtype], n_seg, S, _ptr(ct),
+                                              float(payload_mass), float(payload_threshold), _ptr(q), _ptr(qd),
+                                              _ptr(qdd), _ptr(tau), _ptr(mask), _ptr(ff), _stream_ptr()))
         first = int(ff.item())
     return {"q": q, "qd": qd, "qdd": qdd, "tau": tau, "feasible": mask, "first_fail": first}
 
@@ -327,7 +341,8 @@ def ik_batch(rot9, trans3, free, want_sols: bool = True, want_status: bool = Tru
 
 
 def ik_select(rot9, trans3, free, q_ref, payload_mass: float = 0.0, mode: str = "rne", q_lo=None, q_hi=None,
-              payload_threshold: float = PAYLOAD_THRESHOLD_TEST, norm: str = "inf"):
+              payload_threshold: float = PAYLOAD_THRESHOLD_TEST, norm: str = "inf",
+              model: Optional[InertialModel] = None):
     """Goal-IK selection (tcmp_ik_select): per pose, the IK solution of the free-joint sweep that is inside the
     joint limits, passes the static torque test ``mode`` and is nearest to ``q_ref`` ([7][n] or [7]).
     Returns (best_q [7][n], best_cost [n] (+inf = none), n_valid int32 [n]); CUDA tensors in -> CUDA tensors out,
@@ -351,9 +366,10 @@ def ik_select(rot9, trans3, free, q_ref, payload_mass: float = 0.0, mode: str = 
         best = torch.empty((7, n), dtype=torch.float64, device=dev)
         cost = torch.empty((n,), dtype=torch.float64, device=dev)
         nv = torch.empty((n,), dtype=torch.int32, device=dev)
-        check(lib.tcmp_ik_select(n, _ptr(r), _ptr(t), _ptr(f), n_free, bcast, _ptr(ref), rb, _nptr(lo), _nptr(hi),
-                                 MODE[mode], float(payload_mass), float(payload_threshold),
-                                 int(norm in ("inf", "max")), _ptr(best), _ptr(cost), _ptr(nv), _stream_ptr()))
+        check(lib.tcmp_ik_select_model(_mptr(model), n, _ptr(r), _ptr(t), _ptr(f), n_free, bcast, _ptr(ref), rb,
+                                       _nptr(lo), _nptr(hi), MODE[mode], float(payload_mass),
+                                       float(payload_threshold), int(norm in ("inf", "max")), _ptr(best),
+                                       _ptr(cost), _ptr(nv), _stream_ptr()))
     if host:
         return best.cpu().numpy(), cost.cpu().numpy(), nv.cpu().numpy()
     return best, cost, nv
@@ -417,7 +433,8 @@ def collision_batch(q, obstacles, q_lo=None, q_hi=None, payload_radius: float = 
 
 
 def extend_prefix(q1, q2, resolution, obstacles, payload_mass: float = 0.0, mode: str = "rne", q_lo=None,
-                  q_hi=None, payload_radius: float = 0.0, payload_threshold: float = PAYLOAD_THRESHOLD_TEST):
+                  q_hi=None, payload_radius: float = 0.0, payload_threshold: float = PAYLOAD_THRESHOLD_TEST,
+                  model: Optional[InertialModel] = None):
     """Safe-prefix length of every candidate RRT* edge q1 -> q2 (tcmp_extend_prefix): extend steps generated,
     collision-checked and (if collision-free) statically torque-tested on the device.
     q1/q2 ``[7][n_edges]`` -> (n_steps int32 [n_edges], prefix int32 [n_edges])."""
@@ -433,10 +450,10 @@ def extend_prefix(q1, q2, resolution, obstacles, payload_mass: float = 0.0, mode
         b = _as_dev(q2, "f64", (7, n), dev)
         ns = torch.empty((n,), dtype=torch.int32, device=dev)
         pre = torch.empty((n,), dtype=torch.int32, device=dev)
-        check(lib.tcmp_extend_prefix(MODE[mode], n, _ptr(a), _ptr(b), _nptr(res), sc.n,
-                                     ctypes.addressof(sc.obs), _nptr(sc.lo), _nptr(sc.hi), sc.payload_radius,
-                                     float(payload_mass), float(payload_threshold), _ptr(ns), _ptr(pre),
-                                     _stream_ptr()))
+        check(lib.tcmp_extend_prefix_model(_mptr(model), MODE[mode], n, _ptr(a), _ptr(b), _nptr(res), sc.n,
+                                           ctypes.addressof(sc.obs), _nptr(sc.lo), _nptr(sc.hi), sc.payload_radius,
+                                           float(payload_mass), float(payload_threshold), _ptr(ns), _ptr(pre),
+                                           _stream_ptr()))
     if host:
         return ns.cpu().numpy(), pre.cpu().numpy()
     return ns, pre

@@ -51,7 +51,9 @@ def _soa(confs):
 
 
 def _make_test(problem, mode, mass_fn):
-    """Common body of the four factories: scalar closure + batched twin over tcmp_rne_batch."""
+    """Common body of the four factories: scalar closure + batched twin over tcmp_rne_batch.  A ``problem.model``
+    (engine.InertialModel; not a reference field) makes every check of the plan use that inertial set."""
+    model = getattr(problem, "model", None)
 
     def batch(confs, ptotalMass=None, velocities=None, accelerations=None):
         q = _soa(confs)
@@ -61,7 +63,7 @@ def _make_test(problem, mode, mass_fn):
         dyn = mode != "nov" and velocities is not None and accelerations is not None
         qd = _soa(velocities) if dyn else None
         qdd = _soa(accelerations) if dyn else None
-        _, ok = engine.torque_test_batch(q, qd, qdd, m, mode=mode, want_tau=False)
+        _, ok = engine.torque_test_batch(q, qd, qdd, m, mode=mode, want_tau=False, model=model)
         return ok.astype(bool)
 
     def test(poses=None, ptotalMass=None, velocities=None, accelerations=None):
@@ -73,7 +75,8 @@ def _make_test(problem, mode, mass_fn):
     test.batch = batch
     test.mode = mode
     test.mass = lambda: mass_fn(None)
-    test.limits = TAU_MAX.copy()
+    test.model = model
+    test.limits = TAU_MAX.copy() if model is None else model.torque_limit.copy()
     return test
 
 
@@ -163,7 +166,8 @@ def get_dynamics_fn_v5(problem, resolutions):
         m_coeff, move_time, num_intervals = _plan(path)
         mode = getattr(torque_fn, "mode", "rne")
         mass = torque_fn.mass() if hasattr(torque_fn, "mass") else 0.0
-        out = engine.traj_feasibility(coefficients_for_kernel(m_coeff), num_intervals, mass, mode=mode)
+        model = getattr(torque_fn, "model", None)
+        out = engine.traj_feasibility(coefficients_for_kernel(m_coeff), num_intervals, mass, mode=mode, model=model)
         n = out["feasible"].shape[0]
         q = out["q"].T.cpu().numpy()
         arrays = getattr(dynam_fn, "as_arrays", False)
@@ -178,7 +182,7 @@ def get_dynamics_fn_v5(problem, resolutions):
         if want_log_torques:
             # Conf.__init__'s logging pass (utils.py:3376-3378): rne WITHOUT payload on the same samples
             log = engine.traj_feasibility(coefficients_for_kernel(m_coeff), num_intervals, 0.0, mode="rne",
-                                          want_samples=False)
+                                          want_samples=False, model=model)
             res["log_tau"] = log["tau"].T.cpu().numpy()
         return res
 
@@ -280,7 +284,8 @@ def planner_fn_force_aware(start_conf, pose, problem, batch=0, collision_backend
         print("Approach path failure")
         return None
     # torques logged per sample by Conf (utils.py:3376-3378): rne without payload, batched in one launch
-    log_tau = _rne_mod.rne_batch(_soa(approach_path), _soa(approach_vels), _soa(approach_accels), 0.0).T
+    log_tau = _rne_mod.rne_batch(_soa(approach_path), _soa(approach_vels), _soa(approach_accels), 0.0,
+                                 model=getattr(problem, "model", None)).T
     if as_arrays:
         return {"q": np.asarray(approach_path), "qd": np.asarray(approach_vels), "qdd": np.asarray(approach_accels),
                 "torques": log_tau, "ts": np.asarray(approach_dts)}

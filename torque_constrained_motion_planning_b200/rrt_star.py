@@ -121,7 +121,8 @@ def _fused_prefix(sequence, collision, torque):
     from . import engine
     q1 = np.asarray(sequence.q1, dtype=float).reshape(7, 1)
     q2 = np.asarray(sequence.q2, dtype=float).reshape(7, 1)
-    _, pre = engine.extend_prefix(q1, q2, sequence.resolutions, scene["packed"], torque.mass(), mode=torque.mode)
+    _, pre = engine.extend_prefix(q1, q2, sequence.resolutions, scene["packed"], torque.mass(), mode=torque.mode,
+                                  model=getattr(torque, "model", None))
     keep = int(pre[0])
     out = []
     for q in sequence:
@@ -335,7 +336,7 @@ def rrt_star_force_aware_batched(start, goal, distance_weights, sample, resoluti
         ns, pre = engine.extend_prefix(np.ascontiguousarray(q1.T), np.ascontiguousarray(targets.T), res,
                                        scene.get("packed") or scene["obstacles"], torque_fn.mass(),
                                        mode=torque_fn.mode, q_lo=scene["q_lo"], q_hi=scene["q_hi"],
-                                       payload_radius=scene["payload_radius"])
+                                       payload_radius=scene["payload_radius"], model=getattr(torque_fn, "model", None))
         for b in range(batch):
             if pre[b] == 0:
                 continue

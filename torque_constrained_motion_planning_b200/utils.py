@@ -24,7 +24,8 @@ class Problem:
     """utils.py:86-93 verbatim field set.  ``torque_test`` in {"base", "dyn", "nov", "rne"}; the reference
     default "arne" selects nothing and crashes later (panda_primitives.py:242) -- here it raises at once."""
 
-    def __init__(self, robot, fixed, payload, payload_mass, execution_time, torque_test="arne"):
+    def __init__(self, robot, fixed, payload, payload_mass, execution_time, torque_test="arne", model=None):
+        self.model = model          # not a reference field: engine.InertialModel for a non-stock arm (None = Panda)
         self.robot = robot
         self.fixed = fixed
         self.payload = payload
