@@ -147,6 +147,10 @@ def cpu_baseline_run(n_sample, reps, nthreads=0):
     return n_sample * reps / dt, cores, dt
 
 
+FP64_INSTR_PER_STATE = 669.0          # 419 DFMA + 180 DMUL + 70 DADD in K1's loop body (SASS)
+EXEC_FLOPS_PER_STATE = 2 * 419.0 + 180.0 + 70.0
+
+
 def sample_edges(n, seed):
     """configs[3] distribution: q_a uniform in the joint limits, q_b = clip(q_a + N(0, 0.5^2))."""
     rng = np.random.default_rng(seed)
@@ -507,6 +511,11 @@ def main():
                 "peak_source": "tcmp_fp64_peak DFMA microbenchmark measured in this run (MEASURED_PEAKS.json "
                                "carries no FP64 entry; datasheet 37.2 TFLOP/s)",
                 "flops_per_state": FLOPS_PER_STATE, "kernel": "rne_batch_kernel<double,DYN,!TOOL,tau,mask>",
+                # what the kernel EXECUTES per state (static SASS count of the loop body, scripts/sass_mix.sh):
+                # 419 DFMA + 180 DMUL + 70 DADD; pipe_frac = FP64 instructions issued / the DFMA rate behind `peak`
+                "executed": {"fp64_instr_per_state": FP64_INSTR_PER_STATE, "flops_per_state": EXEC_FLOPS_PER_STATE,
+                             "achieved": EXEC_FLOPS_PER_STATE * N_STATES / kernel_s / 1e12,
+                             "pipe_frac": FP64_INSTR_PER_STATE * N_STATES / kernel_s / (fp64_peak / 2.0)},
                 "kernel_ms": kernel_s * 1e3, "kernel_launches_averaged": k_kernel,
                 "hbm": {"achieved": achieved_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                         "frac": achieved_gbs / peaks.get("hbm_gbs"), "bytes_per_state": BYTES_PER_STATE,

@@ -45,3 +45,31 @@ extern "C" void host_rne_batch(const tcmp_model *model, int mode, int64_t n, con
     if (model) dispatch(mode, n, q, qd, qdd, pm, ps, pt, tau, ok, params_from_desc<double>(*model));
     else dispatch(mode, n, q, qd, qdd, pm, ps, pt, tau, ok, ConstParams());
 }
+
+// ---- K1's table-driven sincos --------------------------------------------------------------------------------
+static const SinCos kTable[kSinCosTableSize] = {
+#include "../../torque_constrained_motion_planning_b200/csrc/sincos_table.inc"
+};
+
+// sin / cos of n angles through the table path (angle j of a state = x[i], the other five zero); ok_out[i] = 0
+// where the fast path declined (|x| >= 4096 or non-finite).
+extern "C" void host_sincos_table(int64_t n, const double *x, double *s_out, double *c_out, uint8_t *ok_out) {
+    for (int64_t i = 0; i < n; ++i) {
+        double q[7] = {0, x[i], 0, 0, 0, 0, 0}, s[7], c[7];
+        ok_out[i] = sincos6_table(q, s, c, kTable);
+        s_out[i] = ok_out[i] ? s[1] : 0.0;
+        c_out[i] = ok_out[i] ? c[1] : 0.0;
+    }
+}
+
+// The compiled-in Panda through rne_core_table (what K1 instantiates), dynamic rne mode.
+extern "C" void host_rne_batch_table(int64_t n, const double *q, const double *qd, const double *qdd, const double *pm,
+                                     double pt, double *tau, uint8_t *ok) {
+    for (int64_t i = 0; i < n; ++i) {
+        double qs[7], vs[7], as[7], t[7];
+        for (int j = 0; j < 7; ++j) { qs[j] = q[j * n + i]; vs[j] = qd[j * n + i]; as[j] = qdd[j * n + i]; }
+        rne_core_table<true, false>(qs, vs, as, pm[i] > pt ? pm[i] : 0.0, 0.0, t, kTable);
+        for (int j = 0; j < 7; ++j) tau[j * n + i] = t[j];
+        ok[i] = within_limits<double>(t);
+    }
+}

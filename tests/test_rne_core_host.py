@@ -22,7 +22,8 @@ def host_rne():
     src = os.path.join(NATIVE, "rne_host.cpp")
     core = os.path.join(ROOT, "torque_constrained_motion_planning_b200", "csrc", "panda_model.cuh")
     hdr = os.path.join(ROOT, "include", "tcmp.h")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in (src, core, hdr)):
+    tab = os.path.join(ROOT, "torque_constrained_motion_planning_b200", "csrc", "sincos_table.inc")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in (src, core, hdr, tab)):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
                                "-o", so, src])
     L = ctypes.CDLL(so)
@@ -106,3 +107,53 @@ def test_model_override_matches_oracle(host_rne, mode):
     tau, ok = host_rne(mode, q, qd, qdd, mass, model=g["model"])
     tau_o, ok_o = oracle.torque_test_batch(mode, q, qd, qdd, mass, model=g["model"])
     assert np.abs(tau - tau_o).max() < 1e-11 and np.array_equal(ok, ok_o)
+
+
+def _table_lib():
+    so = os.path.join(NATIVE, "librne_host.so")
+    return ctypes.CDLL(so)
+
+
+def test_table_sincos_accuracy(host_rne):
+    """K1's table-driven sincos (csrc/sincos_table.inc + two short polynomials) against extended-precision libm:
+    abs error <= 2.5e-16 over the joint range, near multiples of pi/2 (where a relative error would show) and up to
+    the 4096 rad switch-over; beyond it (and for inf / nan) the fast path declines."""
+    L = _table_lib()
+    rng = np.random.default_rng(36)
+    half_pi = np.arange(-40, 41) * (np.pi / 2)
+    x = np.concatenate([rng.uniform(-3.8, 3.8, 400_000), rng.uniform(-4095.9, 4095.9, 200_000),
+                        half_pi, half_pi + 1e-9, half_pi - 3e-13, np.arange(-1024, 1025) * (np.pi / 512),
+                        [0.0, -0.0, 5e-324, 1e-300, 4095.999]])
+    s, c = np.empty_like(x), np.empty_like(x)
+    ok = np.empty(len(x), np.uint8)
+    p = lambda a: a.ctypes.data_as(_dp)
+    L.host_sincos_table(ctypes.c_int64(len(x)), p(x), p(s), p(c), ok.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    assert ok.all()
+    xl = x.astype(np.longdouble)
+    es = np.abs(s - np.sin(xl)).max()
+    ec = np.abs(c - np.cos(xl)).max()
+    assert es < 2.5e-16 and ec < 2.5e-16, (es, ec)
+    assert np.abs(s * s + c * c - 1).max() < 5e-16
+    far = np.array([4096.0, -5000.0, 1e300, np.inf, -np.inf, np.nan])
+    s2, c2, ok2 = np.empty_like(far), np.empty_like(far), np.empty(len(far), np.uint8)
+    L.host_sincos_table(ctypes.c_int64(len(far)), p(far), p(s2), p(c2), ok2.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    assert not ok2.any()
+
+
+def test_table_path_torques_match_oracle_and_reference(host_rne):
+    L = _table_lib()
+    q, qd, qdd, mass = sample_states(50_000, seed=37)
+    q[4, ::97] += 5000.0                              # some states take the libm fallback
+    tau = np.empty((7, q.shape[1]))
+    ok = np.empty(q.shape[1], np.uint8)
+    p = lambda a: np.ascontiguousarray(a).ctypes.data_as(_dp)
+    L.host_rne_batch_table(ctypes.c_int64(q.shape[1]), p(q), p(qd), p(qdd), p(mass), ctypes.c_double(0.01), p(tau),
+                           ok.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    tau_o, ok_o = oracle.torque_test_batch("rne", q, qd, qdd, mass)
+    assert np.abs(tau - tau_o).max() < 1e-11 and np.array_equal(ok, ok_o)
+    g = load_golden("states_cfg2.npz")
+    n = g["q"].shape[1]
+    tau, ok = np.empty((7, n)), np.empty(n, np.uint8)
+    L.host_rne_batch_table(ctypes.c_int64(n), p(g["q"]), p(g["qd"]), p(g["qdd"]), p(g["mass"]), ctypes.c_double(0.01),
+                           p(tau), ok.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    assert np.abs(tau - g["tau_rne"]).max() < 1e-11 and np.array_equal(ok, g["feasible_rne"])

@@ -438,11 +438,40 @@ TCMP_FN void sincos6(const T (&q)[7], T (&s)[7], T (&c)[7]) {
     for (int j = 1; j < 7; ++j) sincos_t<T>(q[j], &s[j], &c[j]);
 }
 
+// Table-driven form of the same (K1 only; fp64).  x = k h + r with h = pi/512 and k = rint(x / h): (sin, cos)(k h)
+// come from a 1024-entry table of correctly rounded values (csrc/sincos_table.inc, staged in shared memory -- the
+// lookup runs on the LSU, not the FP64 pipe), and |r| <= 3.1e-3 needs only r - r^3/6 + r^5/120 and
+// 1 - r^2/2 + r^4/24 (truncation < 2e-18).  14 FP64 instructions per angle instead of 21; worst abs error 2.3e-16
+// (tests/test_rne_core_host.py).  Valid while k h1 is exact, i.e. |x| < 4096 rad; any larger or non-finite angle
+// sends the whole state down CUDA's sincos() as before.
+struct alignas(16) SinCos { double s, c; };
+constexpr int kSinCosTableSize = 1024;
+TCMP_FN bool sincos6_table(const double (&q)[7], double (&s)[7], double (&c)[7], const SinCos *__restrict__ tab) {
+    bool fast = true;
+#pragma unroll
+    for (int j = 1; j < 7; ++j) fast = fast && ((hi_word(q[j]) & 0x7fffffff) < 0x40b00000);   // |x| < 4096
+    if (!fast) return false;
+#pragma unroll
+    for (int j = 1; j < 7; ++j) {
+        const double kt = fma(q[j], 162.97466172610082 /* 512 / pi */, 6755399441055744.0);   // rint via 1.5 * 2^52
+        const SinCos e = tab[lo_word(kt) & (kSinCosTableSize - 1)];
+        const double kd = kt - 6755399441055744.0;
+        // pi/512 = h1 + h2 + ...: fdlibm's 33-bit pieces of pi/2 scaled by 2^-8 (k < 2^20 keeps k h1, k h2 exact)
+        double r = fma(-kd, 1.57079632673412561417e+00 / 256, q[j]);
+        r = fma(-kd, 6.07710050630396597660e-11 / 256, r);
+        const double z = r * r;
+        const double sl = fma(r * z, fma(z, 1.0 / 120, -1.0 / 6), r);      // sin r
+        const double cm = z * fma(z, 1.0 / 24, -0.5);                      // cos r - 1
+        s[j] = fma(e.c, sl, fma(e.s, cm, e.s));                            // sin(kh) cos r + cos(kh) sin r
+        c[j] = fma(-e.s, sl, fma(e.c, cm, e.c));                           // cos(kh) cos r - sin(kh) sin r
+    }
+    return true;
+}
+
+// The recursion proper, given sin / cos of joints 2..7 (s[0], c[0] are never read).
 template <typename T, bool DYN, bool TOOL, typename P = ConstParams>
-TCMP_FN void rne_core(const T (&q)[7], const T (&qd)[7], const T (&qdd)[7], T mp_inertial,
-                                         T mp_tool, T (&tau)[7], const P &p = P()) {
-    T c[7], s[7];
-    sincos6<T>(q, s, c);
+TCMP_FN void rne_body(const T (&s)[7], const T (&c)[7], const T (&qd)[7], const T (&qdd)[7], T mp_inertial,
+                      T mp_tool, T (&tau)[7], const P &p = P()) {
 
     V3<T> F[7], N[7];
     Kin<T> k;
@@ -509,6 +538,26 @@ TCMP_FN void rne_core(const T (&q)[7], const T (&qd)[7], const T (&qdd)[7], T mp
         else t0 += p.jzz0 * qdd[0];
     }
     tau[0] = t0;
+}
+
+template <typename T, bool DYN, bool TOOL, typename P = ConstParams>
+TCMP_FN void rne_core(const T (&q)[7], const T (&qd)[7], const T (&qdd)[7], T mp_inertial, T mp_tool, T (&tau)[7],
+                      const P &p = P()) {
+    T c[7], s[7];
+    sincos6<T>(q, s, c);
+    rne_body<T, DYN, TOOL, P>(s, c, qd, qdd, mp_inertial, mp_tool, tau, p);
+}
+
+// K1's form: sin / cos from the shared-memory table when every angle allows it.
+template <bool DYN, bool TOOL>
+TCMP_FN void rne_core_table(const double (&q)[7], const double (&qd)[7], const double (&qdd)[7], double mp_inertial,
+                            double mp_tool, double (&tau)[7], const SinCos *__restrict__ tab) {
+    double c[7], s[7];
+    if (!sincos6_table(q, s, c, tab)) {
+#pragma unroll
+        for (int j = 1; j < 7; ++j) sincos_t<double>(q[j], &s[j], &c[j]);
+    }
+    rne_body<double, DYN, TOOL, ConstParams>(s, c, qd, qdd, mp_inertial, mp_tool, tau);
 }
 
 // |tau_i| < limit_i for i in 0..5 (panda_primitives.py:182-183; joint 7 is never tested).
