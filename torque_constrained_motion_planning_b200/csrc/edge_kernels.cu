@@ -21,6 +21,12 @@ template <typename T> __device__ __forceinline__ T linspace_sample(int i, int n,
     return (T)t;
 }
 
+// (sin, cos)(i pi / 512) for the table-driven sincos of the dynamic fp64 edge kernel (see rne_kernels.cu / panda_model.cuh
+// sincos6_table); this translation unit carries its own read-only copy (no relocatable device code in the build).
+static __device__ const SinCos kEdgeSinCosTable[kSinCosTableSize] = {
+#include "sincos_table.inc"
+};
+
 // Multi-GPU form: lane 0 stores the edge's first-failure index into the gathered buffer of every rank (peer
 // pointers over NVLink, see tcmp_rne_batch_scatter) instead of a local array + a separate NCCL all-gather.
 struct IndexDests {
@@ -35,6 +41,13 @@ __global__ void __launch_bounds__(128)
 edge_kernel(int64_t n_edges, int W, double interval, double step, const T *__restrict__ qa,
             const T *__restrict__ qb, T mass, T payload_threshold, int32_t *__restrict__ first_fail,
             IndexDests dests, const __grid_constant__ P prm) {
+    // compiled-in Panda, fp64, dynamic: the same table-driven sincos as K1 (14 instead of 21 FP64 instr / angle)
+    constexpr bool kTable = sizeof(T) == 8 && DYN && kIsConst<P>;
+    __shared__ SinCos tab[kTable ? kSinCosTableSize : 1];
+    if constexpr (kTable) {
+        for (int t = threadIdx.x; t < kSinCosTableSize; t += blockDim.x) tab[t] = kEdgeSinCosTable[t];
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -67,7 +80,8 @@ edge_kernel(int64_t n_edges, int W, double interval, double step, const T *__res
                     as[j] = A[j] * pa;
                 }
             }
-            rne_core<T, DYN, TOOL, P>(qs, vs, as, mp_inertial, mp_tool, tau, prm);
+            if constexpr (kTable) rne_core_table<DYN, TOOL>(qs, vs, as, mp_inertial, mp_tool, tau, tab);
+            else rne_core<T, DYN, TOOL, P>(qs, vs, as, mp_inertial, mp_tool, tau, prm);
             const unsigned fails = __ballot_sync(0xffffffffu, active && !limits_ok<T, P>(tau, prm));
             if (fails) {
                 first = base + __ffs(fails) - 1;
