@@ -513,6 +513,9 @@ def main():
                 "flops_per_state": FLOPS_PER_STATE, "kernel": "rne_batch_kernel<double,DYN,!TOOL,tau,mask>",
                 # what the kernel EXECUTES per state (static SASS count of the loop body, scripts/sass_mix.sh):
                 # 419 DFMA + 180 DMUL + 70 DADD; pipe_frac = FP64 instructions issued / the DFMA rate behind `peak`
+                "note": "achieved / frac use SURVEY 8d's ALGORITHMIC 1654 FLOP per state; the kernel executes 1088 "
+                        "(customised recursion, regrouped parameters, table-driven sincos), so frac can reach 1 "
+                        "while the FP64 pipe is at executed.pipe_frac",
                 "executed": {"fp64_instr_per_state": FP64_INSTR_PER_STATE, "flops_per_state": EXEC_FLOPS_PER_STATE,
                              "achieved": EXEC_FLOPS_PER_STATE * N_STATES / kernel_s / 1e12,
                              "pipe_frac": FP64_INSTR_PER_STATE * N_STATES / kernel_s / (fp64_peak / 2.0)},
