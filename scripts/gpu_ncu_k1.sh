@@ -1,8 +1,9 @@
 #!/bin/bash
-set -x
+# ncu evidence for K1 on the current build: launch list of a short bench run, then one --set full capture.
+# Each ncu pass only after the same command exited 0 without it.
 mkdir -p gpurun_out
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:rne_batch_kernel -s 3 -c 2 -f -o gpurun_out/prof_rne_final \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
+$CMD > gpurun_out/plain.log 2>&1 || { tail -5 gpurun_out/plain.log; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rne_batch_kernel -s 3 -c 2 -f -o gpurun_out/prof_rne $CMD > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log | cut -c1-160
