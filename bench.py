@@ -505,9 +505,9 @@ def main():
                 "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                 "frac": achieved_tf / (fp64_peak / 1e12),
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, from the ncu --set full
-                # capture in profiles/r01/ncu_full_rne_batch_kernel_final_raw.csv (168.0 MB read + 26.8 MB written at
+                # capture in profiles/r01/ncu_full_rne_batch_kernel_final_raw.csv (168.0 MB read + 24.9 MB written at
                 # kernel end; the remaining dirty lines are still in the 126 MB L2) -- <= 233 MB algorithmic
-                "traffic": 194.8e6,
+                "traffic": 192.9e6,
                 "peak_source": "tcmp_fp64_peak DFMA microbenchmark measured in this run (MEASURED_PEAKS.json "
                                "carries no FP64 entry; datasheet 37.2 TFLOP/s)",
                 "flops_per_state": FLOPS_PER_STATE, "kernel": "rne_batch_kernel<double,DYN,!TOOL,tau,mask>",
