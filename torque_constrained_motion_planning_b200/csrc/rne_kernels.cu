@@ -6,7 +6,7 @@
 // Data layout: structure-of-arrays [7][n] so that the 32 lanes of a warp read 32 consecutive
 // elements of each joint row (one 256 B request per row per warp, fully coalesced).  Loads are
 // streaming (ld.global.cs) and stores are st.global.cs: every byte is touched exactly once.
-// Bound: FP64 pipe: 233 B and ~600 FP64 instructions per state.
+// Bound: FP64 pipe, with HBM close behind: 233 B and 669 FP64 instructions per state (rne).
 #include "panda_model.cuh"
 #include "tcmp_internal.h"
 
@@ -16,7 +16,7 @@ namespace tcmp {
 // locally and letting a separate NCCL all-gather move it, every thread stores its mask byte straight into
 // the gathered buffer of EVERY rank (peer pointers mapped over NVLink/NVSwitch, CUDA IPC) at
 // dest_offset + i.  1 B/state/peer of NVLink traffic rides under an FP64-bound kernel; no extra launch,
-// no host-side collective call (which costs more CPU time than this 63 us kernel runs).
+// no host-side collective call (which costs more CPU time than this ~45 us kernel runs).
 #ifndef TCMP_PDL
 #define TCMP_PDL 1
 #endif
@@ -77,7 +77,7 @@ rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T
 #if TCMP_PDL
     // Programmatic dependent launch: let the next launch on this stream become resident while this grid's
     // last wave drains (its CTAs then sit in griddepcontrol.wait), so back-to-back batches do not pay the
-    // launch + ramp-up gap (~5 % of a 63 us kernel).  Stream-order semantics are kept: nothing is read or
+    // launch + ramp-up gap (~5 % of the kernel).  Stream-order semantics are kept: nothing is read or
     // written before the wait, which returns only when every earlier grid has completed and flushed.
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
