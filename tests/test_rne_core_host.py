@@ -157,3 +157,38 @@ def test_table_path_torques_match_oracle_and_reference(host_rne):
     L.host_rne_batch_table(ctypes.c_int64(n), p(g["q"]), p(g["qd"]), p(g["qdd"]), p(g["mass"]), ctypes.c_double(0.01),
                            p(tau), ok.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
     assert np.abs(tau - g["tau_rne"]).max() < 1e-11 and np.array_equal(ok, g["feasible_rne"])
+
+
+def test_structural_properties_of_the_recursion(host_rne):
+    """Size-independent properties the domain offers, on the product's own recursion (host build):
+    joint 1's angle never matters (gravity is along its axis: bit-identical), zero velocities through the dynamic
+    path equal the static path, torques are affine in the payload mass, and doubling every mass and inertia of the
+    model doubles the static torques."""
+    q, qd, qdd, _ = sample_states(4000, seed=38)
+    q2 = q.copy()
+    q2[0] = np.random.default_rng(39).uniform(-2.8, 2.8, q.shape[1])
+    a, _ = host_rne("rne", q, qd, qdd, 3.0)
+    b, _ = host_rne("rne", q2, qd, qdd, 3.0)
+    assert np.array_equal(a, b)
+    z = np.zeros_like(q)
+    dyn0, _ = host_rne("rne", q, z, z, 3.0)
+    stat, _ = host_rne("rne", q, None, None, 3.0)
+    nov, _ = host_rne("nov", q, qd, qdd, 3.0)
+    assert np.abs(dyn0 - stat).max() < 1e-12 and np.array_equal(stat, nov)
+    t1, _ = host_rne("rne", q, qd, qdd, 1.0)
+    t3, _ = host_rne("rne", q, qd, qdd, 3.0)
+    t5, _ = host_rne("rne", q, qd, qdd, 5.0)
+    assert np.abs(t1 + t5 - 2 * t3).max() < 1e-11
+    m = oracle.default_model()
+    f = oracle.model_fields(m)
+    base, _ = host_rne("nov", q, None, None, 0.0, model=m)
+    f["mass"] *= 2.0
+    f["inertia"] *= 2.0
+    twice, _ = host_rne("nov", q, None, None, 0.0, model=m)
+    assert np.abs(twice - 2 * base).max() < 1e-11
+    # dyn mode: the payload enters only through the tool-point force, so tau(dyn, m) - tau(rne, 0) is linear in m
+    d0, _ = host_rne("dyn", q, qd, qdd, 0.0)
+    d2, _ = host_rne("dyn", q, qd, qdd, 2.0)
+    d4, _ = host_rne("dyn", q, qd, qdd, 4.0)
+    r0, _ = host_rne("rne", q, qd, qdd, 0.0)
+    assert np.abs(d0 - r0).max() < 1e-12 and np.abs((d4 - d0) - 2 * (d2 - d0)).max() < 1e-11
