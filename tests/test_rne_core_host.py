@@ -192,3 +192,20 @@ def test_structural_properties_of_the_recursion(host_rne):
     d4, _ = host_rne("dyn", q, qd, qdd, 4.0)
     r0, _ = host_rne("rne", q, qd, qdd, 0.0)
     assert np.abs(d0 - r0).max() < 1e-12 and np.abs((d4 - d0) - 2 * (d2 - d0)).max() < 1e-11
+
+
+def test_sincos_table_is_what_the_generator_produces():
+    """csrc/sincos_table.inc is generated (scripts/make_sincos_table.py, 70-digit arithmetic): regenerate and compare
+    every entry bit for bit; exact zeros / ones sit at the quadrant points."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_sincos_table", os.path.join(ROOT, "scripts", "make_sincos_table.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    path = os.path.join(ROOT, "torque_constrained_motion_planning_b200", "csrc", "sincos_table.inc")
+    rows = [l.strip().strip("{},").split(", ") for l in open(path) if l.startswith("{")]
+    assert len(rows) == 1024
+    for i in range(0, 1024, 7):      # every 7th entry keeps the test under a second; the quadrant points below too
+        s, c = gen.entry(i)
+        assert (float.fromhex(rows[i][0]), float.fromhex(rows[i][1])) == (s, c), i
+    for i, (s, c) in {0: (0.0, 1.0), 256: (1.0, 0.0), 512: (0.0, -1.0), 768: (-1.0, 0.0)}.items():
+        assert (float.fromhex(rows[i][0]), float.fromhex(rows[i][1])) == (s, c)
