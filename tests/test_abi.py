@@ -87,3 +87,30 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.TcmpError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/tcmp.h is a C interface: it must compile as C99 (and as C++11) on its own, warnings as errors, and a C
+    program linked against libtcmp.so must resolve and run the CUDA-free entry points."""
+    import subprocess
+    from conftest import ROOT
+    src = tmp_path / "use_tcmp.c"
+    src.write_text('#include <stdio.h>\n#include "tcmp.h"\n'
+                   'int main(void) {\n'
+                   '    tcmp_model m; double lim[7];\n'
+                   '    if (tcmp_abi_version() != TCMP_ABI_VERSION) return 1;\n'
+                   '    if (tcmp_model_default(&m) != 0 || m.mass[8] != 0.68) return 2;\n'
+                   '    if (tcmp_get_limits(lim, 0, 0, 0) != 0 || lim[0] != 87.0) return 3;\n'
+                   '    if (tcmp_rne_batch(9, 0, 1, 0, 0, 0, 0, 0.0, 0.01, 0, 0, 0) == 0) return 4;\n'
+                   '    printf("%s\\n", tcmp_last_error());\n'
+                   '    return 0;\n}\n')
+    inc = os.path.join(ROOT, "include")
+    for cc, std in (("/usr/bin/gcc", "-std=c99"), ("/usr/bin/g++", "-std=c++11")):
+        subprocess.check_call([cc, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc] +
+                              (["-x", "c++"] if cc.endswith("g++") else []) + [str(src)])
+    exe = tmp_path / "use_tcmp"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ltcmp",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "bad mode" in out.stdout, (out.returncode, out.stdout, out.stderr)
