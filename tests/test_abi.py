@@ -114,3 +114,26 @@ def test_header_is_plain_c(tmp_path):
                            "-Wl,-rpath," + libdir])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "bad mode" in out.stdout, (out.returncode, out.stdout, out.stderr)
+
+
+def test_product_never_reaches_into_the_oracle():
+    """The checker is test infrastructure: no module of the product imports it, no native source includes it, and
+    importing the whole package leaves `oracle` out of sys.modules (run in a fresh interpreter)."""
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "torque_constrained_motion_planning_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.sep + "build" in dirpath:
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            text = open(os.path.join(dirpath, f)).read()
+            assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), f
+            assert not re.search(r'#include\s+"[^"]*oracle', text), f
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import torque_constrained_motion_planning_b200 as p\n"
+            "from torque_constrained_motion_planning_b200 import (engine, rne, ikfast_panda_arm, ik_utils, ikfast,\n"
+            "    franka_ik_fast, min_jerk_v2, utils, collision, rrt_star, panda_primitives, panda_model, distributed)\n"
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'\n" % ROOT)
+    subprocess.check_call([sys.executable, "-c", code])
