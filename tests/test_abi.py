@@ -137,3 +137,20 @@ def test_product_never_reaches_into_the_oracle():
             "    franka_ik_fast, min_jerk_v2, utils, collision, rrt_star, panda_primitives, panda_model, distributed)\n"
             "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'\n" % ROOT)
     subprocess.check_call([sys.executable, "-c", code])
+
+
+def test_library_carries_sm_100a_code_for_every_kernel_family():
+    """libtcmp.so embeds native sm_100a cubins (no PTX-only JIT path, no other architectures) with the kernels the
+    design names."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elfs = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    cubins = re.findall(r"(\w+)\.(sm_\w+)\.cubin", elfs)
+    assert cubins and {arch for _, arch in cubins} == {"sm_100a"}, elfs
+    usage = subprocess.run([cuobjdump, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for kernel in ("rne_batch_kernel", "rne_model_kernel", "edge_kernel", "traj_kernel", "ik_kernel_compact",
+                   "fk_kernel", "ik_select_kernel", "collision_kernel", "extend_prefix_kernel", "fp64_peak_kernel"):
+        assert kernel in usage, kernel
