@@ -9,6 +9,7 @@ extern "C" void host_ik_batch(int64_t n, const double *rot9, const double *trans
                               int n_free, int free_broadcast, double *sols_out, int32_t *count_out,
                               uint8_t *status_out) {
     using namespace tcmp::ik;
+#pragma omp parallel for schedule(static)
     for (int64_t p = 0; p < n; ++p)
         for (int f = 0; f < n_free; ++f) {
             double R[9];

@@ -17,14 +17,18 @@ NATIVE = os.path.join(ROOT, "tests", "native")
 _dp = ctypes.POINTER(ctypes.c_double)
 
 
-@pytest.fixture(scope="module")
-def host_ik():
-    so = os.path.join(NATIVE, "libik_host.so")
+def _build_host_ik(name, defines=()):
+    so = os.path.join(NATIVE, name)
     src = os.path.join(NATIVE, "ik_host.cpp")
     core = os.path.join(ROOT, "torque_constrained_motion_planning_b200", "csrc", "ik_core.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
-    L = ctypes.CDLL(so)
+    tab = os.path.join(ROOT, "torque_constrained_motion_planning_b200", "csrc", "sincos_table.inc")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in (src, core, tab)):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off"] +
+                              ["-D" + d for d in defines] + ["-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def _wrap_host_ik(L):
 
     def fn(rot, trans, free):
         rot, trans, free = (np.ascontiguousarray(a, dtype=np.float64) for a in (rot, trans, free))
@@ -38,6 +42,17 @@ def host_ik():
                         st.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
         return sols, c, st
     return fn
+
+
+@pytest.fixture(scope="module")
+def host_ik():
+    return _wrap_host_ik(_build_host_ik("libik_host.so"))
+
+
+@pytest.fixture(scope="module")
+def host_ik_table():
+    """The same source with TCMP_IK_TABLE_SINCOS=1 (table-driven sin / cos of the solved joints; default off)."""
+    return _wrap_host_ik(_build_host_ik("libik_host_table.so", ["TCMP_IK_TABLE_SINCOS=1"]))
 
 
 def angular_match(sols, ref, count):
@@ -80,3 +95,24 @@ def test_special_value_sweep_counts_bit_exact(host_ik):
     # values: well-conditioned solves to 1e-9; singular neighbourhoods only to the solver's own ~1e-6
     worst = max(angular_match(s[i], sr[i], cr[i]) for i in np.nonzero(cr > 0)[0][:1200])
     assert worst < 1e-6, worst
+
+
+def test_table_sincos_variant_keeps_every_solution_count(host_ik_table):
+    """TCMP_IK_TABLE_SINCOS=1: the solver's decisions hang on residuals compared with 1e-5 .. 1e-7, the table's sin /
+    cos differ from libm's by <= 2.3e-16 -- 1.5 M solves over random reachable poses and the special-value poses of
+    the golden set must give the reference's counts exactly and its solutions to 1e-9."""
+    if not oracle.have_ref():
+        pytest.skip("compiled reference IKFast not present")
+    g = load_golden("ik_cfg3.npz")
+    s, c, st = host_ik_table(g["special_rot"], g["special_trans"], g["special_free"])
+    assert (c == g["special_counts"]).all()
+    rng = np.random.default_rng(81)
+    n, nf = 60_000, 25
+    q = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, n))
+    trans, rot = oracle.ref_fk_batch(q)
+    free = np.vstack([q[6:7], rng.uniform(Q_LO[6], Q_HI[6], size=(nf - 1, n))])
+    sols_r, counts_r = oracle.ref_ik_batch(rot, trans, free)
+    sols, counts, status = host_ik_table(rot, trans, free)
+    assert np.array_equal(counts, counts_r) and (status == 0).all()
+    idx = np.nonzero(counts_r)[0][::97]
+    assert max(angular_match(sols[i], sols_r[i], counts_r[i]) for i in idx) < 1e-9

@@ -41,8 +41,60 @@
 #define TCMP_ROOT_LOOP
 #endif
 
+// TCMP_IK_TABLE_SINCOS = 1 (default 0, candidate for the next round): sin / cos of the solved joint angles from the
+// 1024-entry table K1 uses (csrc/sincos_table.inc; x = k pi/512 + r, two short polynomials in r, abs error 2.3e-16)
+// instead of libm's sincos -- a fraction of the inlined code of a kernel that stalls on instruction fetch.  The
+// solution COUNT must not move: tests/test_ik_core_host.py soaks the host build of this variant against the
+// compiled reference solver.  The table is read through the read-only cache on the device.
+#ifndef TCMP_IK_TABLE_SINCOS
+#define TCMP_IK_TABLE_SINCOS 0
+#endif
+#include <string.h>
+
 namespace tcmp {
 namespace ik {
+
+#if TCMP_IK_TABLE_SINCOS
+struct alignas(16) SinCosEntry { double s, c; };
+#ifdef __CUDACC__
+static __device__ const SinCosEntry kSinCosDev[1024] = {
+#include "sincos_table.inc"
+};
+#endif
+static const SinCosEntry kSinCosHost[1024] = {
+#include "sincos_table.inc"
+};
+#endif
+
+// sin and cos of one angle: the table path while |x| < 4096 rad (every angle the solver produces), libm otherwise.
+TCMP_HD inline void sincos_ik(double x, double *s, double *c) {
+#if TCMP_IK_TABLE_SINCOS
+    int64_t bits;
+    memcpy(&bits, &x, 8);
+    if (((int)(bits >> 32) & 0x7fffffff) < 0x40b00000) {
+        const double kt = fma(x, 162.97466172610082 /* 512 / pi */, 6755399441055744.0);   // rint via 1.5 * 2^52
+        int64_t kb;
+        memcpy(&kb, &kt, 8);
+        const int idx = (int)(kb & 1023);
+#ifdef __CUDA_ARCH__
+        const double2 e2 = __ldg(reinterpret_cast<const double2 *>(kSinCosDev) + idx);
+        const double es = e2.x, ec = e2.y;
+#else
+        const double es = kSinCosHost[idx].s, ec = kSinCosHost[idx].c;
+#endif
+        const double kd = kt - 6755399441055744.0;
+        double r = fma(-kd, 1.57079632673412561417e+00 / 256, x);
+        r = fma(-kd, 6.07710050630396597660e-11 / 256, r);
+        const double z = r * r;
+        const double sl = fma(r * z, fma(z, 1.0 / 120, -1.0 / 6), r);
+        const double cm = z * fma(z, 1.0 / 24, -0.5);
+        *s = fma(ec, sl, fma(es, cm, es));
+        *c = fma(-es, sl, fma(ec, cm, ec));
+        return;
+    }
+#endif
+    sincos(x, s, c);
+}
 
 constexpr double kPi = 3.14159265358979;      // IKPI   (ikfast_panda_arm.cpp:68) -- truncated on purpose
 constexpr double k2Pi = 6.28318530717959;     // IK2PI  (:67)
@@ -91,7 +143,7 @@ struct Root {
 };
 TCMP_HD TCMP_OUTLINE inline Root make_root(double angle) {
     Root r;
-    sincos(angle, &r.s, &r.c);
+    sincos_ik(angle, &r.s, &r.c);
     r.a = wrap_pi(angle);
     return r;
 }
@@ -151,7 +203,12 @@ TCMP_HD TCMP_OUTLINE inline void solve_shoulder(const Pose &P, const Root &j3, c
     const double cj1 = M[2][2];
     if (cj1 >= -1 - kSinCosThresh && cj1 <= 1 + kSinCosThresh) {
         const double a = clamp_acos(cj1);
+#if TCMP_IK_TABLE_SINCOS
+        double s, c_unused;
+        sincos_ik(a, &s, &c_unused);
+#else
         const double s = sin(a);
+#endif
         j1r[0] = {a, s, cj1};
         j1r[1] = {-a, -s, cj1};
         j1ok[0] = j1ok[1] = true;
@@ -249,7 +306,7 @@ TCMP_HD inline void prepare_pose(const double R[9], double tx, double ty, double
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) P.r[i][j] = R[i * 3 + j];
     P.j6 = j6;
-    sincos(j6, &P.s6, &P.c6);
+    sincos_ik(j6, &P.s6, &P.c6);
     P.px = tx + (-0.107) * P.r[0][2];
     P.py = (-0.107) * P.r[1][2] + ty;
     P.pz = -0.333 + tz + (-0.107) * P.r[2][2];
