@@ -209,3 +209,25 @@ def test_sincos_table_is_what_the_generator_produces():
         assert (float.fromhex(rows[i][0]), float.fromhex(rows[i][1])) == (s, c), i
     for i, (s, c) in {0: (0.0, 1.0), 256: (1.0, 0.0), 512: (0.0, -1.0), 768: (-1.0, 0.0)}.items():
         assert (float.fromhex(rows[i][0]), float.fromhex(rows[i][1])) == (s, c)
+
+
+def test_special_joint_values(host_rne):
+    """Joint values snapped to multiples of pi/4 and to the joint limits (exact table nodes of the table-driven sincos,
+    zeros of sin / cos): the polynomial path, the table path and the run-time model path all stay on the oracle."""
+    from conftest import Q_HI, Q_LO
+    rng = np.random.default_rng(40)
+    q, qd, qdd, mass = sample_states(30_000, seed=41)
+    snap = rng.random(q.shape) < 0.5
+    q = np.where(snap, np.clip(np.round(q / (np.pi / 4)) * (np.pi / 4), Q_LO[:, None], Q_HI[:, None]), q)
+    tau_o, ok_o = oracle.torque_test_batch("rne", q, qd, qdd, mass)
+    tau, ok = host_rne("rne", q, qd, qdd, mass)
+    assert np.abs(tau - tau_o).max() < 1e-11 and np.array_equal(ok, ok_o)
+    tau, ok = host_rne("rne", q, qd, qdd, mass, model=oracle.default_model())
+    assert np.abs(tau - tau_o).max() < 1e-11 and np.array_equal(ok, ok_o)
+    L = _table_lib()
+    n = q.shape[1]
+    tau, ok = np.empty((7, n)), np.empty(n, np.uint8)
+    p = lambda a: np.ascontiguousarray(a).ctypes.data_as(_dp)
+    L.host_rne_batch_table(ctypes.c_int64(n), p(q), p(qd), p(qdd), p(mass), ctypes.c_double(0.01), p(tau),
+                           ok.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    assert np.abs(tau - tau_o).max() < 1e-11 and np.array_equal(ok, ok_o)
