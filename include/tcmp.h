@@ -150,6 +150,10 @@ int tcmp_edge_feasibility_scatter(int mode, int64_t n_edges, int n_waypoints, co
  *   q_out/qd_out/qdd_out/tau_out [7][n_seg*S], feasible_out [n_seg*S],
  *   first_fail_out[1] = first infeasible sample or n_seg*S.  first_fail_out must be
  *   initialised by the caller to n_seg*S (the kernel atomicMin's into it).
+ *   TCMP_MODE_BASE (the constant-true test, panda_primitives.py:13-16): feasible_out is all 1, first_fail_out is
+ *   not touched, and q_out / qd_out / qdd_out / tau_out are still written -- the samples are the trajectory the
+ *   planner returns and tau_out holds the rne torques (payload_scalar as given) that Conf logs for every sample
+ *   regardless of the test mode (utils.py:3376-3378).
  */
 int tcmp_traj_feasibility(int mode, int dtype, int n_seg, int samples_per_segment,
                           const double *coeffs, double payload_scalar, double payload_threshold,
@@ -164,10 +168,18 @@ int tcmp_traj_feasibility(int mode, int dtype, int n_seg, int samples_per_segmen
  *   free_vals [n_free][n], or [n_free] when free_broadcast != 0;
  *   solve index s = pose*n_free + f;  sols_out [n*n_free][8][7] (may be NULL: counts only),
  *   count_out [n*n_free] = number of solutions (0..8).
- *   status_out [n*n_free] or NULL: bit 0 = the solve entered a singular branch of the reference's decision tree
- *   (resolved like the reference: shoulder singularity, j2 pinned to 0); bit 1 = a special case of the generated
- *   solver that is not implemented (never observed on 100 M random + special-value solves); bit 2 = non-finite
- *   input (the reference throws from IKFAST_ASSERT; here the solve returns 0 solutions).
+ *   status_out [n*n_free] or NULL:
+ *     bit 0 (1) = the solve entered a singular branch of the reference's decision tree.  With bit 1 clear the
+ *       branch was RESOLVED the way the reference resolves it: shoulder singularity (j2 pinned to 0, :3209-3325),
+ *       elbow singularity at j4 = 2.63084142381503 (one member of the one-parameter family, :2774-2835) and at
+ *       j4 = 0 (:2436-2598), wrist centre on the joint-6 axis (:509-2346 -- no arm configuration reaches such a
+ *       pose and every leaf of that sub-tree rejects it: 0 solutions).
+ *     bit 1 (2) = the solve reached a branch of the generated solver that this library does NOT implement and the
+ *       solutions of that branch were dropped: the count may be lower than the reference's.  Those branches need an
+ *       input that is not a rigid transform (a rotation matrix off orthonormal by more than ~1e-6) or a floating-point
+ *       tie on a 1e-6 guard; none is reached by the structured singular-pose sweeps of tests/ (profiles/r02/
+ *       ik_reference_coverage.md lists the reference's reached lines).
+ *     bit 2 (4) = non-finite input (the reference throws from IKFAST_ASSERT; here the solve returns 0 solutions).
  */
 int tcmp_ik_batch(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
                   int n_free, int free_broadcast, double *sols_out, int32_t *count_out,

@@ -177,7 +177,7 @@ def test_fused_final_check_matches_per_sample_reference_semantics():
     assert out["feasible"] == (len(bad) == 0)
 
 
-@pytest.mark.parametrize("mode,mass", [("rne", 1.0), ("nov", 1.0), ("rne", 5.0)])
+@pytest.mark.parametrize("mode,mass", [("rne", 1.0), ("nov", 1.0), ("rne", 5.0), ("base", 1.0)])
 def test_planner_fn_force_aware_end_to_end(mode, mass):
     """BASELINE configs 1/5 in miniature: the demo scene (test_planner.py:36-54 as boxes), start conf
     utils.py:45, goal pose = FK of a reachable configuration.  The GPU planner must return exactly what the
@@ -211,9 +211,13 @@ def test_planner_fn_force_aware_end_to_end(mode, mass):
     qd = np.array([c_.velocities for c_ in traj.path]).T
     qdd = np.array([c_.accelerations for c_ in traj.path]).T
     # every sample passes the reference torque test, and the logged torques are rne WITHOUT payload
-    _, ok = oracle.torque_test_batch(mode, np.ascontiguousarray(q), np.ascontiguousarray(qd),
-                                     np.ascontiguousarray(qdd), mass)
-    assert ok.all()
+    # (`base` is the constant-true test: nothing to pass, but the samples and logged torques must still be real --
+    # the trajectory kernel used to leave them unwritten in this mode)
+    assert np.isfinite(q).all() and np.abs(q[:, 0] - np.array(start)).max() < 1e-12
+    if mode != "base":
+        _, ok = oracle.torque_test_batch(mode, np.ascontiguousarray(q), np.ascontiguousarray(qd),
+                                         np.ascontiguousarray(qdd), mass)
+        assert ok.all()
     tau0, _ = oracle.torque_test_batch("rne", np.ascontiguousarray(q), np.ascontiguousarray(qd),
                                        np.ascontiguousarray(qdd), 0.0)
     assert np.abs(np.array([c_.torques for c_ in traj.path]).T - tau0).max() < 1e-9

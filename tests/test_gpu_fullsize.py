@@ -100,3 +100,47 @@ def test_config4_hundred_thousand_edges(eng):
     ff = eng.edge_feasibility(dev(qa), dev(qb), 64, 5.0, mode="rne")
     assert np.array_equal(ff.cpu().numpy(), ff_o)
     assert 0.6 < (ff_o == 64).mean() < 0.9
+
+
+def test_structured_singular_pose_families_five_million_solves(eng):
+    """every joint at 0, +-pi/2, +-pi/4, +-3pi/4, +-pi and its limits, joint 4 at +-2.63084142381503 (the
+    elbow singularity, ikfast_panda_arm.cpp:2774-2835) and at 0 (:2436-2598), singly, in pairs, mixed, perturbed by
+    1e-5 .. 1e-9, plus poses built with the shoulder centre on the joint-6 axis (:506-508) -- > 5 M solves through
+    tcmp_ik_batch.  Solution COUNT bit-exact against the compiled, unmodified reference; status bit 1 ("branch not
+    implemented, solutions dropped") never set; every solution of the elbow-singular families reproduces its pose."""
+    import torch
+    from ik_families import structured_families, wrist_axis_family
+    total = flagged = 0
+    for name, (q, free) in structured_families(n_per=26_000, seed=11).items():
+        trans, rot = oracle.ref_fk_batch(q)
+        _, cr = oracle.ref_ik_batch(rot, trans, free, want_sols=False, nthreads=NT)
+        sols, counts, status = eng.ik_batch(dev(rot), dev(trans), dev(free))
+        c, st = counts.cpu().numpy(), status.cpu().numpy()
+        mism = np.nonzero(c != cr)[0]
+        assert len(mism) == 0, (name, len(mism), mism[:5], c[mism[:5]], cr[mism[:5]])
+        assert (st & 2 == 0).all(), name
+        assert (st & 0xf8 == 0).all(), name                 # the internal redo marker never leaves the library
+        _, counts2, _ = eng.ik_batch(dev(rot), dev(trans), dev(free), want_sols=False)     # counts-only kernels
+        assert torch.equal(counts2, counts), name
+        total += len(c)
+        flagged += int((st & 1).sum())
+        if name in ("j4_sing_p", "j4_sing_p_special", "j4_zero_pm1e-06", "pin_j2_j4"):
+            nf = free.shape[0]
+            valid = torch.arange(8, device="cuda")[None, :] < counts[:, None]
+            qs = sols[valid].T.contiguous()
+            t2, r2 = eng.fk_batch(qs)
+            idx = torch.nonzero(valid)[:, 0] // nf
+            assert (t2 - dev(trans)[:, idx]).abs().max().item() < 1e-6, name
+            assert (r2 - dev(rot)[:, idx]).abs().max().item() < 1e-6, name
+    assert total >= 5_000_000 and flagged > 100_000
+    rot, trans, free = wrist_axis_family(200_000)
+    _, cr = oracle.ref_ik_batch(rot, trans, free, want_sols=False, nthreads=NT)
+    _, counts, status = eng.ik_batch(dev(rot), dev(trans), dev(free), want_sols=False)
+    assert np.array_equal(counts.cpu().numpy(), cr) and (cr == 0).all()
+    assert int((status & 2).max()) == 0
+    # VERDICT r01 "what's weak" #1: reference 6, round-1 build 4
+    q = np.array([[0.3, -0.5, 0.7, 2.63084142381503, 0.4, 1.9, -0.6]]).T
+    trans, rot = oracle.ref_fk_batch(q)
+    _, cr = oracle.ref_ik_batch(rot, trans, np.array([[-0.6]]))
+    _, counts, status = eng.ik_batch(dev(rot), dev(trans), dev(np.array([[-0.6]])))
+    assert cr[0] == 6 and int(counts[0]) == 6 and int(status[0]) == 1

@@ -302,14 +302,18 @@ def test_scatter_kernel_single_rank(eng):
     q, qd, qdd, mass = sample_states(n, seed=21)
     buf = PeerMaskBuffer(n)
     assert buf.world == 1 and buf.gathered.shape == (1, n)
+    seen = []
     for mode in ["rne", "nov", "dyn", "base"]:
-        buf.gathered.zero_()
+        buf._slots.zero_()
         tau = buf.torque_test(dev(q), dev(qd), dev(qdd), dev(mass), mode=mode)
         buf.barrier()
+        seen.append(buf.gathered.data_ptr())
         tau_o, ok_o = oracle.torque_test_batch(mode, q, qd, qdd, mass)
         assert np.array_equal(buf.gathered[0].cpu().numpy(), ok_o)
         if mode != "base":
             assert np.abs(tau.cpu().numpy() - tau_o).max() < TOL64
+    # consecutive steps alternate between the two copies of the gathered buffer (read -> next-write ordering)
+    assert seen[0] != seen[1] and seen[0] == seen[2] and seen[1] == seen[3]
     buf.close()
 
 
@@ -441,6 +445,19 @@ def test_traj_kernel_other_modes(eng, mode):
     tau_o, mask_o, ff_o = oracle.traj_feasibility(mode, t["points"], int(t["n_int"]), float(t["mass"]))
     assert np.abs(out["tau"].cpu().numpy().T - tau_o).max() < TOL64
     assert np.array_equal(out["feasible"].cpu().numpy(), mask_o) and out["first_fail"] == ff_o
+
+
+def test_traj_kernel_base_mode_writes_samples_and_log_torques(eng):
+    """TCMP_MODE_BASE (constant-true test): mask all 1, first_fail = n, and q / qd / qdd / tau are the same samples and
+    rne torques the rne mode writes (the planner returns them as the trajectory; ADVICE r01, edge_kernels.cu)."""
+    t = load_golden("traj.npz")
+    coeffs = oracle.minjerk_coefficients(t["points"])
+    base = eng.traj_feasibility(coeffs, int(t["n_int"]), float(t["mass"]), mode="base")
+    rne = eng.traj_feasibility(coeffs, int(t["n_int"]), float(t["mass"]), mode="rne")
+    n = base["feasible"].shape[0]
+    assert bool(base["feasible"].all()) and base["first_fail"] == n
+    for k in ("q", "qd", "qdd", "tau"):
+        assert np.array_equal(base[k].cpu().numpy(), rne[k].cpu().numpy()), k
 
 
 def test_edge_kernel_fp32_path(eng):

@@ -97,6 +97,65 @@ def test_special_value_sweep_counts_bit_exact(host_ik):
     assert worst < 1e-6, worst
 
 
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_structured_singular_families_counts_bit_exact(host_ik):
+    """Every joint at 0, +-pi/2, +-pi/4, +-3pi/4, +-pi and its limits, joint 4 at +-2.63084142381503 (the elbow
+    singularity the generated solver special-cases, ikfast_panda_arm.cpp:2774-2835) and at 0 (:2436-2598), singly, in
+    pairs, mixed and perturbed by 1e-5 .. 1e-9: the solution COUNT equals the compiled reference's on every solve and
+    no solve reports an unimplemented branch.  VERDICT r01 repro included."""
+    from ik_families import structured_families, wrist_axis_family
+    total = 0
+    for name, (q, free) in structured_families(n_per=1500, seed=11).items():
+        trans, rot = oracle.ref_fk_batch(q)
+        sr, cr = oracle.ref_ik_batch(rot, trans, free)
+        s, c, st = host_ik(rot, trans, free)
+        assert np.array_equal(c, cr), (name, np.nonzero(c != cr)[0][:5])
+        assert (st & 2 == 0).all(), name
+        total += len(c)
+        if name in ("j4_sing_p", "j4_sing_p_special"):
+            assert (st & 1).sum() >= q.shape[1]            # the elbow branch is entered on every own-j7 solve
+            # every returned solution -- including the member of the one-parameter family the solver picks at the
+            # elbow singularity -- reproduces the pose
+            idx = np.nonzero(c > 0)[0][:400]
+            for i in idx:
+                p = i // free.shape[0]
+                t2, r2 = oracle.ref_fk_batch(np.ascontiguousarray(s[i, :c[i]].T))
+                assert np.abs(t2 - trans[:, p:p + 1]).max() < 1e-6 and np.abs(r2 - rot[:, p:p + 1]).max() < 1e-6
+    assert total > 200_000
+    rot, trans, free = wrist_axis_family(4000)
+    _, cr = oracle.ref_ik_batch(rot, trans, free)
+    _, c, st = host_ik(rot, trans, free)
+    assert np.array_equal(c, cr) and (cr == 0).all() and (st & 2 == 0).all() and (st & 1).sum() > 1000
+    # VERDICT r01 "what's weak" #1
+    q = np.array([[0.3, -0.5, 0.7, 2.63084142381503, 0.4, 1.9, -0.6]]).T
+    trans, rot = oracle.ref_fk_batch(q)
+    _, cr = oracle.ref_ik_batch(rot, trans, np.array([[-0.6]]))
+    _, c, st = host_ik(rot, trans, np.array([[-0.6]]))
+    assert cr[0] == 6 and c[0] == 6 and st[0] == 1
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_non_rigid_inputs_flag_every_dropped_branch(host_ik):
+    """Inputs that are not rigid transforms (rotation off orthonormal by 1e-8 .. 1e-5) can reach special cases of the
+    generated solver that are not built (its polynomial-root fall-backs, :3335-9540): the count may then be lower
+    than the reference's, and status bit 1 must say so on EVERY such solve."""
+    from ik_families import structured_families
+    rng = np.random.default_rng(0)
+    mism = total = 0
+    for name, (q, free) in structured_families(n_per=600, seed=21).items():
+        trans, rot = oracle.ref_fk_batch(q)
+        for eps in (1e-8, 1e-6, 1e-5):
+            r2 = rot + rng.normal(0, eps, size=rot.shape)
+            t2 = trans + rng.normal(0, eps, size=trans.shape)
+            _, cr = oracle.ref_ik_batch(r2, t2, free)
+            _, c, st = host_ik(r2, t2, free)
+            bad = c != cr
+            assert not (bad & ((st & 2) == 0)).any(), name
+            mism += int(bad.sum())
+            total += len(c)
+    assert mism < 2e-3 * total
+
+
 def test_table_sincos_variant_keeps_every_solution_count(host_ik_table):
     """TCMP_IK_TABLE_SINCOS=1: the solver's decisions hang on residuals compared with 1e-5 .. 1e-7, the table's sin /
     cos differ from libm's by <= 2.3e-16 -- 1.5 M solves over random reachable poses and the special-value poses of

@@ -238,7 +238,19 @@ static cudaError_t launch_traj_typed(int mode, int n_seg, int S, const double *c
 cudaError_t launch_traj_feasibility(int mode, int dtype, int n_seg, int S, const double *coeffs, double ps,
                                     double pt, void *q, void *qd, void *qdd, void *tau, uint8_t *mask,
                                     int32_t *ff, cudaStream_t st, const tcmp_model *model) {
-    if (mode == TCMP_MODE_BASE) {  // constant-true test: only the mask is defined
+    if (mode == TCMP_MODE_BASE) {
+        // Constant-true test (panda_primitives.py:13-16): the verdict is all-feasible and first_fail is left alone,
+        // but the samples are still the trajectory the planner returns, and Conf logs rne torques for them whatever
+        // the test mode (utils.py:3376-3378) -- so q / qd / qdd / tau are written by the rne kernel.
+        if (q || qd || qdd || tau) {
+            const cudaError_t e =
+                dtype == TCMP_F64
+                    ? launch_traj_typed<double>(TCMP_MODE_RNE, n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, nullptr, nullptr,
+                                                model, st)
+                    : launch_traj_typed<float>(TCMP_MODE_RNE, n_seg, S, coeffs, ps, pt, q, qd, qdd, tau, nullptr, nullptr,
+                                               model, st);
+            if (e != cudaSuccess) return e;
+        }
         return mask ? launch_fill<uint8_t>((int64_t)n_seg * S, mask, 1, st) : cudaSuccess;
     }
     if (dtype == TCMP_F64)

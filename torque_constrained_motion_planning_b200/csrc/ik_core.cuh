@@ -165,9 +165,11 @@ struct Emit {
 };
 
 enum : unsigned {
-    kStatusDegenerate = 1u,  // a singular branch of the decision tree was entered (and resolved if bit 1 is clear)
-    kStatusUnresolved = 2u,  // ... one of the generated solver's special cases this restatement does not implement
-    kStatusInvalid = 4u      // non-finite target: the reference trips IKFAST_ASSERT (:57,:138) and throws; here 0 solutions
+    kStatusDegenerate = 1u,  // a singular branch of the decision tree was entered (and resolved like the reference if bit 1 is clear)
+    kStatusUnresolved = 2u,  // ... a branch of the generated solver this restatement does not implement: solutions dropped
+    kStatusInvalid = 4u,     // non-finite target: the reference trips IKFAST_ASSERT (:57,:138) and throws; here 0 solutions
+    kStatusRedo = 128u       // internal (never leaves the kernels): solve_one_t<false> met the elbow singularity and wants
+                             // the complete tree (solve_one_t<true>, a separate cold region of the kernel) to redo the solve
 };
 
 TCMP_HD inline void emit_solution(Emit &out, double j0, double j1, double j2, double j3, double j4,
@@ -268,7 +270,9 @@ TCMP_ROOT_LOOP
                 continue;
         }
         if (fabs(M[2][0]) + fabs(M[2][1]) < kBranchThresh) {  // (:9601-9605); sin(j1) already tested
-            out.status |= kStatusDegenerate;
+            // M20^2 + M21^2 = sin^2 j1 for a rotation matrix, so this needs a non-orthonormal input: the generated
+            // special cases behind it (:9607-12470) are not implemented
+            out.status |= kStatusDegenerate | kStatusUnresolved;
             continue;
         }
         if (!atan2_checked(M[2][1], -M[2][0], &at)) continue;
@@ -325,8 +329,66 @@ TCMP_HD inline int screen_pose(const Pose &P) {
     return in_unit(arg3) ? 1 : 0;
 }
 
-// One solve (IKSolver::ComputeIk, :412).
-TCMP_HD inline void solve_one(const Pose &P, Emit &out) {
+// Elbow singularity (:2409-2850): K = -0.0825 + 0.0825 cos j3 + 0.316 sin j3 ~ 0 at j3 ~ 0 (forearm and upper-arm axes
+// collinear) and at j3 ~ 2 atan(0.316 / 0.0825) = 2.63084142381503 (shoulder centre on the forearm axis).  The solver
+// falls through two more guard levels -- products of q0 with U and W, which are below the threshold whenever the first
+// level tripped on a consistent pose -- and then matches j3 against the two special angles.
+// Returns the number of j4 candidates written to j4c (0..2); *j3 is overwritten when the solver pins it.
+TCMP_HD TCMP_OUTLINE inline int solve_elbow_singular(const Pose &P, Root *j3p, const Root &j5, double q0, double U,
+                                                     double W, Root j4c[2], Emit &out) {
+    const Root j3 = *j3p;
+    // second / third guard level (:2415-2417, :2427-2429): j4eval[1] = U q0 and -11.36.. W q0 (expanded in the
+    // generated code); their else-branches (:2853-3030, alternative atan2 forms of j4) need K == 0 with q0 != 0.
+    if (!(fabs(q0) < kBranchThresh || fabs(U * q0) < kBranchThresh) ||
+        !(fabs(q0) < kBranchThresh || fabs(11.3636363636364 * W * q0) < kBranchThresh)) {
+        out.status |= kStatusUnresolved;
+        return 0;
+    }
+    const double Wn = (-P.npz) * j5.s + j5.c * (P.npy * P.s6) + 0.088 * j5.c - j5.c * (P.c6 * P.npx);   // -W (:2445)
+    const double near0 = -3.14159265358979 + pos_fmod(3.14159265358979 + fabs(j3.a), 6.28318530717959);
+    const double nearS = -3.14159265358979 +
+                         pos_fmod(3.14159265358979 + fabs(-2.63084142381503 + j3.a), 6.28318530717959);
+    if (fabs(near0) < kAngleThresh) {
+        // j3 ~ 0 (:2436-2598): the solver pins j3 = 0 (sin 0, cos 1).  A consistent pose has U = W = 0 here and the
+        // solver gives up ("no branches": j4 and j2 turn about the same line); only a pose whose (U, W) residue lies
+        // between 1e-6 and 1e-5 gets the two opposite j4 roots of atan2(U, -W).
+        if (fabs(U) + fabs(Wn) < kBranchThresh) return 0;
+        double at;
+        if (!atan2_checked(U, Wn, &at)) return 0;
+        *j3p = Root{0.0, 0.0, 1.0};
+        const Root j4r[2] = {make_root(-at), make_root(3.14159265358979 - at)};
+        const bool j4ok[2] = {true, !same_root(j4r[0], j4r[1])};
+        int n4 = 0;
+        for (int i4 = 0; i4 < 2; ++i4) {
+            if (!j4ok[i4]) continue;
+            if (fabs(j4r[i4].c * Wn - j4r[i4].s * U) > kEvalThresh) continue;   // (:2583)
+            j4c[n4++] = j4r[i4];
+        }
+        return n4;
+    }
+    if (fabs(nearS) < kAngleThresh) {
+        // j3 ~ 2.63084 (:2774-2835): every j4 solves the position equations and the spherical shoulder absorbs the
+        // rotation about the forearm axis -- a one-parameter family.  The solver evaluates its general formula with
+        // K frozen at -3.85e-10 (the value of its rounded sin / cos literals), i.e. j4 = atan2(-U, -W) of whatever
+        // residue the pose carries, and keeps that single member of the family.
+        const double y = (-2597402597.4026) * U;
+        const double x = 2597402597.4026 * Wn;
+        if (fabs(y) < kAtan2Thresh && fabs(x) < kAtan2Thresh && fabs(y * y + x * x - 1) <= kSinCosThresh) return 0;
+        const Root j4 = make_root(isnan(y) ? kPi2 : (isnan(x) ? 0.0 : atan2(y, x)));
+        const double e0 = -U - 3.85e-10 * j4.s, e1 = Wn - 3.85e-10 * j4.c, e2 = j4.s * Wn + j4.c * U,
+                     e3 = -3.85e-10 + j4.c * Wn - j4.s * U;
+        if (fabs(e0) > kEvalThresh || fabs(e1) > kEvalThresh || fabs(e2) > kEvalThresh || fabs(e3) > kEvalThresh) return 0;
+        j4c[0] = j4;
+        return 1;
+    }
+    return 0;   // "branch miss [j4]" (:2849): K ~ 0 away from both special angles cannot happen for real j3
+}
+
+// One solve (IKSolver::ComputeIk, :412).  WITH_ELBOW = false is the kernels' hot path: it carries everything but the
+// elbow-singularity branches (1 solve in ~10^5 of a random sweep, every solve of a pose with joint 4 at 2.63084 / 0) and
+// bails out with kStatusRedo when it meets one; inlining those branches costs the hot path 36 registers (128 -> 164).
+template <bool WITH_ELBOW>
+TCMP_HD inline void solve_one_t(const Pose &P, Emit &out) {
     const double cn = P.c6 * P.npx;  // x78
     const double sn = P.npy * P.s6;  // x79
     // j3 from |p|^2 (:461-485)
@@ -352,7 +414,14 @@ TCMP_ROOT_LOOP
         const double x975 = 0.088 - cn + sn;
         const double g1 = fabs(x975) + fabs(P.npz);
         if (fabs(g0) < kBranchThresh || fabs(g1) < kBranchThresh) {
-            out.status |= kStatusDegenerate;   // wrist centre on the joint-6 axis
+            // Shoulder centre within 8.8e-5 m of the joint-6 axis (g0 = 129.13 h^2, h the distance).  The generated
+            // sub-tree (:509-2346) solves j4 from asin(U / K) first and j5 from a quotient by h^2, but each of its j5
+            // formulas is guarded by the same g0 (times 1, sin j4 or cos j4) and ends in "no branches", and its doubly
+            // singular part (:516-1575, j3 ~ 2.63084 as well) needs |2.6e9 U| <= 1 where |U| = 0.068 on this axis.
+            // The geometry agrees: 0.384 + 0.316 cos j3 - 0.0825 sin j3 >= 0.057 > h, no configuration puts the
+            // shoulder there.  So: 0 solutions, resolved (the compiled reference returns 0 on every such pose of
+            // scripts/ik_structured_families.py:wrist_axis_family).
+            out.status |= kStatusDegenerate;
             continue;
         }
         // j5: two roots (:2347-2386)
@@ -378,24 +447,39 @@ TCMP_ROOT_LOOP
             const double W = (-0.088) * j5.c - j5.c * sn + P.npz * j5.s + j5.c * cn;
             const double q0 = -1.0 + j3.c + 3.83030303030303 * j3.s;
             const double sK = sign_of(K);
+            Root j3u = j3, j4c[2];
+            int n4;
             if (fabs(q0) < kBranchThresh || fabs(U) + fabs(W) < kBranchThresh || fabs(sK) < kBranchThresh) {
-                out.status |= kStatusDegenerate;   // elbow offset cancels / j4 axis through the wrist
-                continue;
-            }
-            double at4;
-            if (!atan2_checked(U, W, &at4)) continue;
-            const Root j4 = make_root(-kHalfPiLit + at4 + kHalfPiLit * (1.0 / sK));
-            {
+                // Elbow singularity: K = 0, the shoulder centre lies on the forearm (joint-5) axis, so the position
+                // equations say nothing about j4 (U^2 + W^2 = K^2).
+                out.status |= kStatusDegenerate;
+                if (!WITH_ELBOW) {
+                    out.status |= kStatusRedo;
+                    return;
+                }
+                n4 = solve_elbow_singular(P, &j3u, j5, q0, U, W, j4c, out);
+            } else {
+                double at4;
+                if (!atan2_checked(U, W, &at4)) continue;
+                const Root j4 = make_root(-kHalfPiLit + at4 + kHalfPiLit * (1.0 / sK));
                 // 4 residuals (:3087-3090)
                 const double e0 = j4.s * K - U, e1 = j4.c * K - W, e2 = j4.c * U - j4.s * W,
                              e3 = K - j4.c * W - j4.s * U;
                 if (fabs(e0) > kEvalThresh || fabs(e1) > kEvalThresh || fabs(e2) > kEvalThresh || fabs(e3) > kEvalThresh)
                     continue;
+                j4c[0] = j4;
+                n4 = 1;
             }
-            solve_shoulder(P, j3, j4, j5, out);
+            // one call site: solve_shoulder is by far the largest inlined body of the kernel
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+            for (int i4 = 0; i4 < n4; ++i4) solve_shoulder(P, j3u, j4c[i4], j5, out);
         }
     }
 }
+
+TCMP_HD inline void solve_one(const Pose &P, Emit &out) { solve_one_t<true>(P, out); }
 
 }  // namespace ik
 }  // namespace tcmp

@@ -77,7 +77,10 @@ ik_kernel_compact(int64_t n, int n_free, int free_broadcast, const double *__res
             out.sols = WRITE_SOLS ? rows + lane * kSolRow : nullptr;
             out.count = 0;
             out.status = 0;
-            solve_one(P, out);
+            solve_one_t<false>(P, out);
+            // elbow singularity: ik_redo_kernel finishes this solve with the complete tree (keeping that tree out of
+            // this kernel keeps it at 128 / 150 registers instead of 168)
+            if (out.status & kStatusRedo) out.count = -1;
             if (WRITE_SOLS)
                 for (int k = (out.count < 8 ? out.count : 8) * 7; k < 56; ++k) rows[lane * kSolRow + k] = 0.0;
             count_out[s] = out.count;
@@ -136,6 +139,35 @@ ik_kernel_compact(int64_t n, int n_free, int free_broadcast, const double *__res
     if (qn > 0) solve_batch(qn);
 }
 
+// Second pass of tcmp_ik_batch: the solves ik_kernel_compact marked with count = -1 (elbow singularity met on the hot
+// path) are redone with the complete decision tree.  One lane per solve; the scan reads 4 B per solve (25 M solves:
+// 100 MB, ~20 us), the flagged solves are rare outside hand-built singular sweeps.
+template <bool WRITE_SOLS>
+__global__ void __launch_bounds__(128)
+ik_redo_kernel(int64_t n, int n_free, int free_broadcast, const double *__restrict__ rot9,
+               const double *__restrict__ trans3, const double *__restrict__ free_vals,
+               double *__restrict__ sols_out, int32_t *__restrict__ count_out, uint8_t *__restrict__ status_out) {
+    const int64_t total = n * n_free;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += stride) {
+        if (count_out[s] >= 0) continue;
+        Pose P;
+        load_pose(s, n, n_free, free_broadcast, rot9, trans3, free_vals, P);
+        double sols[56];
+        Emit out;
+        out.sols = WRITE_SOLS ? sols : nullptr;
+        out.count = 0;
+        out.status = 0;
+        solve_one_t<true>(P, out);
+        if (WRITE_SOLS) {
+            const int filled = (out.count < 8 ? out.count : 8) * 7;
+            for (int k = 0; k < 56; ++k) sols_out[s * 56 + k] = k < filled ? sols[k] : 0.0;
+        }
+        count_out[s] = out.count;
+        if (status_out) status_out[s] = (uint8_t)out.status;
+    }
+}
+
 // FK (ComputeFk, :307-395): T = prod_k DH_k(q_k), rows k = 0..7 of the Panda modified-DH table.
 __global__ void __launch_bounds__(256)
 fk_kernel(int64_t n, const double *__restrict__ q, double *__restrict__ trans3, double *__restrict__ rot9) {
@@ -182,10 +214,16 @@ cudaError_t launch_ik_batch(int64_t n, const double *rot9, const double *trans3,
         const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel_compact<true>), ik::kIkBlock, n * n_free);
         ik::ik_kernel_compact<true><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals,
                                                                    sols_out, count_out, status_out);
+        const int grid2 = grid_for(reinterpret_cast<const void *>(ik::ik_redo_kernel<true>), 128, n * n_free);
+        ik::ik_redo_kernel<true><<<grid2, 128, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out,
+                                                        count_out, status_out);
     } else {
         const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel_compact<false>), ik::kIkBlock, n * n_free);
         ik::ik_kernel_compact<false><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals,
                                                                     sols_out, count_out, status_out);
+        const int grid2 = grid_for(reinterpret_cast<const void *>(ik::ik_redo_kernel<false>), 128, n * n_free);
+        ik::ik_redo_kernel<false><<<grid2, 128, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out,
+                                                         count_out, status_out);
     }
     return cudaGetLastError();
 }

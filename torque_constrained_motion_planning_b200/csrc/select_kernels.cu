@@ -67,7 +67,11 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
                 out.sols = sols;
                 out.count = 0;
                 out.status = 0;
-                ik::solve_one(P, out);
+                ik::solve_one_t<false>(P, out);
+                if (out.status & ik::kStatusRedo) {   // elbow singularity: redo with the complete tree (cold region)
+                    out.count = 0;
+                    ik::solve_one_t<true>(P, out);
+                }
                 cnt = out.count < 8 ? out.count : 8;
             }
             int ncand = 0;

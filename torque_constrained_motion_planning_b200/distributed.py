@@ -160,10 +160,19 @@ class PeerMaskBuffer:
     DIRECTLY (tcmp_rne_batch_scatter): the all-gather of the masks fused into the producing kernel as a
     peer-store epilogue over NVLink/NVSwitch.  Each rank allocates its copy with tcmp_peer_alloc (cudaMalloc +
     CUDA IPC), the 64-byte handles are exchanged once through torch.distributed, and peers are mapped with
-    tcmp_peer_open.  After ``torque_test`` + a stream sync + ``barrier()`` every rank holds every mask."""
+    tcmp_peer_open.  After ``torque_test`` + a stream sync + ``barrier()`` every rank holds every mask.
+
+    Ordering protocol.  The buffer has ``SLOTS`` = 2 copies and step i writes copy i % 2, so the one ``barrier()`` per
+    step orders both directions: (write -> read) every rank's stores of step i land before anyone reads copy i % 2;
+    (read -> next write) copy i % 2 is next written by step i + 2, which a peer can only launch after it left
+    barrier i + 1, i.e. after this rank ENTERED barrier i + 1 -- so a consumer must finish reading ``gathered`` of
+    step i before it calls ``barrier()`` for step i + 1 (enqueue the reads on the current stream: ``barrier``
+    synchronises the device first).  With a single copy a fast rank's step i + 1 could overwrite row r of a slower
+    rank's buffer while that rank was still reading step i."""
 
     itemsize = 1
     typestr = "|u1"
+    SLOTS = 2
 
     def __init__(self, n_per_rank: int, group=None):
         import ctypes
@@ -177,7 +186,8 @@ class PeerMaskBuffer:
         if self.world > 8:
             raise ValueError("at most 8 peers (one NVSwitch node)")
         self.n = int(n_per_rank)
-        nbytes = self.n * self.world * self.itemsize
+        nbytes = self.SLOTS * self.n * self.world * self.itemsize
+        self._step = 0
         self._own = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
         self._check(self._lib.tcmp_peer_alloc(ctypes.byref(self._own), nbytes, handle))
@@ -198,8 +208,16 @@ class PeerMaskBuffer:
                 self._peers.append(p)
                 ptrs[r] = p.value
         self._ptrs = ptrs
-        self.gathered = torch.as_tensor(_DevArray(self._own.value, self.n * self.world, self.typestr),
-                                        device=dev).view(self.world, self.n)
+        self._slots = torch.as_tensor(_DevArray(self._own.value, self.SLOTS * self.n * self.world, self.typestr),
+                                      device=dev).view(self.SLOTS, self.world, self.n)
+        self.gathered = self._slots[0]
+
+    def _next_offset(self):
+        """Element offset of this rank's row in the copy the coming step writes; ``gathered`` follows it."""
+        slot = self._step % self.SLOTS
+        self._step += 1
+        self.gathered = self._slots[slot]
+        return (slot * self.world + self.rank) * self.n
 
     def torque_test(self, q, qd=None, qdd=None, payload_mass=0.0, mode="rne", payload_threshold=0.01,
                     want_tau=True, out_tau=None):
@@ -215,7 +233,7 @@ class PeerMaskBuffer:
         ptr = lambda t: None if t is None else int(t.data_ptr())
         self._check(self._lib.tcmp_rne_batch_scatter(
             MODE[mode], DTYPE["f64"], n, ptr(q), ptr(qd), ptr(qdd), ptr(pm), scalar, float(payload_threshold),
-            ptr(tau), self.world, self._ptrs, self.rank * self.n, int(torch.cuda.current_stream().cuda_stream)))
+            ptr(tau), self.world, self._ptrs, self._next_offset(), int(torch.cuda.current_stream().cuda_stream)))
         return tau
 
     def barrier(self):
@@ -230,7 +248,7 @@ class PeerMaskBuffer:
             self._lib.tcmp_peer_close(p)
         self._peers = []
         if self._own:
-            self.gathered = None
+            self.gathered = self._slots = None
             self._lib.tcmp_peer_free(self._own)
             self._own = None
 
@@ -253,5 +271,5 @@ class PeerIndexBuffer(PeerMaskBuffer):
         assert n <= self.n
         self._check(self._lib.tcmp_edge_feasibility_scatter(
             MODE[mode], n, int(n_waypoints), int(qa.data_ptr()), int(qb.data_ptr()), float(payload_mass),
-            float(payload_threshold), int(static_only), self.world, self._ptrs, self.rank * self.n,
+            float(payload_threshold), int(static_only), self.world, self._ptrs, self._next_offset(),
             int(torch.cuda.current_stream().cuda_stream)))
