@@ -42,8 +42,15 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False, defines=(), suffix: str = "") -> str:
-    """defines/suffix build an experimental variant (libtcmp<suffix>.so) next to the product library."""
+# per-source flags of the product build
+SOURCE_FLAGS = {}
+
+
+def build(force: bool = False, verbose: bool = False, defines=(), suffix: str = "", source_flags=None) -> str:
+    """defines/suffix/source_flags build an experimental variant (libtcmp<suffix>.so) next to the product library;
+    source_flags = {"ik_kernels.cu": ["-fmad=false"], ...} is merged over SOURCE_FLAGS."""
+    per_source = dict(SOURCE_FLAGS)
+    per_source.update(source_flags or {})
     lib_path = LIB if not suffix else os.path.join(HERE, "libtcmp%s.so" % suffix)
     if not force and not suffix and not _stale():
         return LIB
@@ -56,8 +63,8 @@ def build(force: bool = False, verbose: bool = False, defines=(), suffix: str = 
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, "-ccbin", ccbin, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, src),
-               "-o", obj]
+        cmd = [nvcc, "-ccbin", ccbin, *NVCC_FLAGS, *per_source.get(src, []), *["-D" + d for d in defines], "-c",
+               os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         log = r.stdout + r.stderr
         with open(os.path.join(objdir, src + ".ptxas.log"), "w") as f:

@@ -96,6 +96,21 @@ TCMP_HD inline void sincos_ik(double x, double *s, double *c) {
     sincos(x, s, c);
 }
 
+// Products and sums that must round exactly like the reference's compiled expressions (g++ -O2 on x86-64: one rounding
+// per operation, no contraction): nvcc fuses a * b + c into an FMA unless told otherwise, and next to a double root of
+// the solver (asin / acos argument within ~1e-12 of +-1) a 1e-16 difference in that argument moves the root by 1e-8 and
+// can flip a duplicate-root or branch test -- i.e. the SOLUTION COUNT.  Everything on the path to such a test (wrist
+// centre, the asin arguments of j3 and j5, U / W / K of j4, the residual rotation M) is written with xmul / xadd in the
+// reference's own association order; the residual checks (compared with 1e-5) are left to the compiler.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+#else
+inline double xmul(double a, double b) { return a * b; }   // host harness: built with -ffp-contract=off
+inline double xadd(double a, double b) { return a + b; }
+#endif
+TCMP_HD inline double xsub(double a, double b) { return xadd(a, -b); }
+
 constexpr double kPi = 3.14159265358979;      // IKPI   (ikfast_panda_arm.cpp:68) -- truncated on purpose
 constexpr double k2Pi = 6.28318530717959;     // IK2PI  (:67)
 constexpr double kPi2 = 1.57079632679490;     // IKPI_2 (:69)
@@ -150,6 +165,15 @@ TCMP_HD TCMP_OUTLINE inline Root make_root(double angle) {
 TCMP_HD inline bool same_root(const Root &x, const Root &y) {  // duplicate-root test (:495)
     return fabs(x.c - y.c) < kSolutionThresh && fabs(x.s - y.s) < kSolutionThresh;
 }
+// A threshold test within 1 % of its threshold.  The values tested next to a double root are sqrt-amplified rounding
+// residue (two roots 1e-6 apart come from an asin / acos argument 1.2e-13 from +-1, where one ulp of the argument moves
+// them by 3e-10), so there the reference's own decision depends on its libm and compiler: the count is ill-conditioned.
+TCMP_HD inline bool near_threshold(double value, double thresh) {
+    return fabs(value - thresh) < 0.01 * thresh;
+}
+TCMP_HD inline bool same_root_borderline(const Root &x, const Root &y) {
+    return near_threshold(fmax(fabs(x.c - y.c), fabs(x.s - y.s)), kSolutionThresh);
+}
 
 struct Pose {
     double r[3][3];
@@ -168,6 +192,8 @@ enum : unsigned {
     kStatusDegenerate = 1u,  // a singular branch of the decision tree was entered (and resolved like the reference if bit 1 is clear)
     kStatusUnresolved = 2u,  // ... a branch of the generated solver this restatement does not implement: solutions dropped
     kStatusInvalid = 4u,     // non-finite target: the reference trips IKFAST_ASSERT (:57,:138) and throws; here 0 solutions
+    kStatusIllConditioned = 8u,  // a duplicate-root or singular-branch test came within 1 % of its threshold: the value
+                                 // tested is amplified rounding residue and the reference's own count depends on its libm
     kStatusRedo = 128u       // internal (never leaves the kernels): solve_one_t<false> met the elbow singularity and wants
                              // the complete tree (solve_one_t<true>, a separate cold region of the kernel) to redo the solve
 };
@@ -190,14 +216,14 @@ TCMP_HD TCMP_OUTLINE inline void solve_shoulder(const Pose &P, const Root &j3, c
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const double ri0 = P.r[i][0], ri1 = P.r[i][1], ri2 = P.r[i][2];
-        const double a = P.c6 * ri0 - P.s6 * ri1;    // x122..x124
-        const double b = -P.s6 * ri0 - P.c6 * ri1;   // x126..x128
-        const double d = ri2 * j5.s + j5.c * a;      // x129..x131
-        const double e = j5.s * a - ri2 * j5.c;      // x125 - r*cj5, x134, x132
-        const double f = j4.c * d - j4.s * b;        // x133 + x120*x126, x135, x136
-        M[i][0] = j3.c * f - j3.s * e;
-        M[i][1] = j4.s * d + j4.c * b;
-        M[i][2] = j3.c * e + j3.s * f;
+        const double a = xsub(xmul(P.c6, ri0), xmul(P.s6, ri1));      // x122..x124
+        const double b = xsub(xmul(-P.s6, ri0), xmul(P.c6, ri1));     // x126..x128
+        const double d = xadd(xmul(ri2, j5.s), xmul(j5.c, a));        // x129..x131
+        const double e = xsub(xmul(j5.s, a), xmul(ri2, j5.c));        // x125 - r*cj5, x134, x132
+        const double f = xsub(xmul(j4.c, d), xmul(j4.s, b));          // x133 + x120*x126, x135, x136
+        M[i][0] = xsub(xmul(j3.c, f), xmul(j3.s, e));
+        M[i][1] = xadd(xmul(j4.s, d), xmul(j4.c, b));
+        M[i][2] = xadd(xmul(j3.c, e), xmul(j3.s, f));
     }
     // j1 = +-acos(M22)  (:3149-3167)
     Root j1r[2];
@@ -218,7 +244,10 @@ TCMP_HD TCMP_OUTLINE inline void solve_shoulder(const Pose &P, const Root &j3, c
         j1r[0] = {0.0, 0.0, 1.0};
         j1ok[0] = true;
     }
-    if (j1ok[0] && j1ok[1] && same_root(j1r[0], j1r[1])) j1ok[1] = false;
+    if (j1ok[0] && j1ok[1]) {
+        if (same_root(j1r[0], j1r[1])) j1ok[1] = false;
+        if (same_root_borderline(j1r[0], j1r[1])) out.status |= kStatusIllConditioned;
+    }
 
 TCMP_ROOT_LOOP
     for (int i1 = 0; i1 < 2; ++i1) {
@@ -226,6 +255,8 @@ TCMP_ROOT_LOOP
         const double j1 = j1r[i1].a, s1 = j1r[i1].s, c1 = j1r[i1].c;
         const double sg = sign_of(s1);
         // general branch requires sin(j1) away from 0 and a usable (M12, M02) pair (:3185-3189)
+        if (near_threshold(fabs(s1), kBranchThresh) || near_threshold(fabs(M[1][2]) + fabs(M[0][2]), kBranchThresh))
+            out.status |= kStatusIllConditioned;
         if (fabs(s1) < kBranchThresh || fabs(M[1][2]) + fabs(M[0][2]) < kBranchThresh || fabs(sg) < kBranchThresh) {
             // Shoulder singularity: joint axes 0 and 2 are collinear, only j0 +- j2 is determined.  The solver
             // resolves it by pinning j2 = 0 (it reports j2 as a free parameter, which get_ik expands with 0,
@@ -311,20 +342,26 @@ TCMP_HD inline void prepare_pose(const double R[9], double tx, double ty, double
         for (int j = 0; j < 3; ++j) P.r[i][j] = R[i * 3 + j];
     P.j6 = j6;
     sincos_ik(j6, &P.s6, &P.c6);
-    P.px = tx + (-0.107) * P.r[0][2];
-    P.py = (-0.107) * P.r[1][2] + ty;
-    P.pz = -0.333 + tz + (-0.107) * P.r[2][2];
-    P.pp = P.px * P.px + P.py * P.py + P.pz * P.pz;
-    P.npx = P.px * P.r[0][0] + P.py * P.r[1][0] + P.pz * P.r[2][0];
-    P.npy = P.px * P.r[0][1] + P.py * P.r[1][1] + P.pz * P.r[2][1];
-    P.npz = P.px * P.r[0][2] + P.py * P.r[1][2] + P.pz * P.r[2][2];
+    P.px = xadd(tx, xmul(-0.107, P.r[0][2]));
+    P.py = xadd(xmul(-0.107, P.r[1][2]), ty);
+    P.pz = xadd(xadd(-0.333, tz), xmul(-0.107, P.r[2][2]));
+    P.pp = xadd(xadd(xmul(P.px, P.px), xmul(P.py, P.py)), xmul(P.pz, P.pz));
+    P.npx = xadd(xadd(xmul(P.px, P.r[0][0]), xmul(P.py, P.r[1][0])), xmul(P.pz, P.r[2][0]));
+    P.npy = xadd(xadd(xmul(P.px, P.r[0][1]), xmul(P.py, P.r[1][1])), xmul(P.pz, P.r[2][1]));
+    P.npz = xadd(xadd(xmul(P.px, P.r[0][2]), xmul(P.py, P.r[1][2])), xmul(P.pz, P.r[2][2]));
+}
+
+// asin argument of j3 (:461-463), in the reference's association order: c0 + c1 pp + (c2 cj6) npx + (c3 npy) sj6
+TCMP_HD inline double j3_asin_argument(const Pose &P) {
+    double t = xadd(0.986881610513004, xmul(-3.89793688895078, P.pp));
+    t = xadd(t, xmul(xmul(0.686036892455338, P.c6), P.npx));
+    return xadd(t, xmul(xmul(-0.686036892455338, P.npy), P.s6));
 }
 
 // The solver's first gate (:461-462): the asin argument of j3.  0 = no solution for this (pose, free value),
 // 1 = continue with solve_one, 2 = non-finite input.  ~45 % of the solves of a free-joint sweep stop here.
 TCMP_HD inline int screen_pose(const Pose &P) {
-    const double arg3 = 0.986881610513004 + (-3.89793688895078) * P.pp + 0.686036892455338 * (P.c6 * P.npx) +
-                        (-0.686036892455338) * (P.npy * P.s6);
+    const double arg3 = j3_asin_argument(P);
     if (!(arg3 == arg3)) return 2;
     return in_unit(arg3) ? 1 : 0;
 }
@@ -344,7 +381,9 @@ TCMP_HD TCMP_OUTLINE inline int solve_elbow_singular(const Pose &P, Root *j3p, c
         out.status |= kStatusUnresolved;
         return 0;
     }
-    const double Wn = (-P.npz) * j5.s + j5.c * (P.npy * P.s6) + 0.088 * j5.c - j5.c * (P.c6 * P.npx);   // -W (:2445)
+    // -W in the association order of :2445: ((-npz sj5) + ((cj5 npy) sj6) + (0.088 cj5)) + ((-cj5 cj6) npx)
+    const double Wn = xadd(xadd(xadd(xmul(-P.npz, j5.s), xmul(xmul(j5.c, P.npy), P.s6)), xmul(0.088, j5.c)),
+                           xmul(xmul(-j5.c, P.c6), P.npx));
     const double near0 = -3.14159265358979 + pos_fmod(3.14159265358979 + fabs(j3.a), 6.28318530717959);
     const double nearS = -3.14159265358979 +
                          pos_fmod(3.14159265358979 + fabs(-2.63084142381503 + j3.a), 6.28318530717959);
@@ -358,6 +397,7 @@ TCMP_HD TCMP_OUTLINE inline int solve_elbow_singular(const Pose &P, Root *j3p, c
         *j3p = Root{0.0, 0.0, 1.0};
         const Root j4r[2] = {make_root(-at), make_root(3.14159265358979 - at)};
         const bool j4ok[2] = {true, !same_root(j4r[0], j4r[1])};
+        if (near_threshold(fabs(U) + fabs(Wn), kBranchThresh)) out.status |= kStatusIllConditioned;
         int n4 = 0;
         for (int i4 = 0; i4 < 2; ++i4) {
             if (!j4ok[i4]) continue;
@@ -371,8 +411,13 @@ TCMP_HD TCMP_OUTLINE inline int solve_elbow_singular(const Pose &P, Root *j3p, c
         // rotation about the forearm axis -- a one-parameter family.  The solver evaluates its general formula with
         // K frozen at -3.85e-10 (the value of its rounded sin / cos literals), i.e. j4 = atan2(-U, -W) of whatever
         // residue the pose carries, and keeps that single member of the family.
-        const double y = (-2597402597.4026) * U;
-        const double x = 2597402597.4026 * Wn;
+        // (:2782-2786) with x1017 = 2597402597.4026 sj6, x1018 = 2597402597.4026 cj6 -- same association order, so the
+        // host build reproduces the reference's j4 (a quotient of rounding residues when K is 0 to the last bit)
+        const double x1017 = xmul(2597402597.4026, P.s6), x1018 = xmul(2597402597.4026, P.c6);
+        const double y = xadd(xmul(-P.npy, x1018), xmul(-P.npx, x1017));
+        const double x = xadd(xadd(xadd(xmul(228571428.571429, j5.c), xmul(xmul(-j5.c, P.npx), x1018)),
+                                   xmul(xmul(-2597402597.4026, P.npz), j5.s)),
+                              xmul(xmul(j5.c, P.npy), x1017));
         if (fabs(y) < kAtan2Thresh && fabs(x) < kAtan2Thresh && fabs(y * y + x * x - 1) <= kSinCosThresh) return 0;
         const Root j4 = make_root(isnan(y) ? kPi2 : (isnan(x) ? 0.0 : atan2(y, x)));
         const double e0 = -U - 3.85e-10 * j4.s, e1 = Wn - 3.85e-10 * j4.c, e2 = j4.s * Wn + j4.c * U,
@@ -389,11 +434,10 @@ TCMP_HD TCMP_OUTLINE inline int solve_elbow_singular(const Pose &P, Root *j3p, c
 // bails out with kStatusRedo when it meets one; inlining those branches costs the hot path 36 registers (128 -> 164).
 template <bool WITH_ELBOW>
 TCMP_HD inline void solve_one_t(const Pose &P, Emit &out) {
-    const double cn = P.c6 * P.npx;  // x78
-    const double sn = P.npy * P.s6;  // x79
+    const double cn = xmul(P.c6, P.npx);  // x78
+    const double sn = xmul(P.npy, P.s6);  // x79
     // j3 from |p|^2 (:461-485)
-    const double arg3 = 0.986881610513004 + (-3.89793688895078) * P.pp + 0.686036892455338 * cn +
-                        (-0.686036892455338) * sn;
+    const double arg3 = j3_asin_argument(P);
     if (!(arg3 == arg3)) {   // NaN anywhere in the pose / free value ends up here
         out.status |= kStatusInvalid;
         return;
@@ -402,6 +446,7 @@ TCMP_HD inline void solve_one_t(const Pose &P, Emit &out) {
     const double a3 = clamp_asin(arg3);
     Root j3r[2] = {make_root(1.10379390314189 + a3), make_root(4.24538655673168 - a3)};
     bool j3ok[2] = {true, !same_root(j3r[0], j3r[1])};
+    if (same_root_borderline(j3r[0], j3r[1])) out.status |= kStatusIllConditioned;
 
 TCMP_ROOT_LOOP
     for (int i3 = 0; i3 < 2; ++i3) {
@@ -411,7 +456,7 @@ TCMP_ROOT_LOOP
         const double g0 = 1.0 + 129.132231404959 * (cn * cn) + 22.7272727272727 * sn + 129.132231404959 * (sn * sn) +
                           (-258.264462809917) * cn * sn + 129.132231404959 * (P.npz * P.npz) +
                           (-22.7272727272727) * cn;
-        const double x975 = 0.088 - cn + sn;
+        const double x975 = xadd(xsub(0.088, cn), sn);
         const double g1 = fabs(x975) + fabs(P.npz);
         if (fabs(g0) < kBranchThresh || fabs(g1) < kBranchThresh) {
             // Shoulder centre within 8.8e-5 m of the joint-6 axis (g0 = 129.13 h^2, h the distance).  The generated
@@ -427,28 +472,33 @@ TCMP_ROOT_LOOP
         // j5: two roots (:2347-2386)
         double at5;
         if (!atan2_checked(P.npz, x975, &at5)) continue;
-        const double h2 = x975 * x975 + P.npz * P.npz;
+        const double h2 = xadd(xmul(x975, x975), xmul(P.npz, P.npz));
         if (h2 < -0.00001) continue;
         const double h = fabs(h2 <= 0.0 ? 0.0 : sqrt(h2));   // IKabs(IKsqrt(.)) (:183)
         if (h == 0.0) continue;                              // IKPowWithIntegerCheck(.,-1) (:269)
-        const double arg5 = (1.0 / h) * (0.384 + (-0.0825) * j3.s + 0.316 * j3.c);
+        const double arg5 = xmul(1.0 / h, xadd(xadd(0.384, xmul(-0.0825, j3.s)), xmul(0.316, j3.c)));
         if (!in_unit(arg5)) continue;
         const double a5 = clamp_asin(arg5);
         Root j5r[2] = {make_root(-a5 - at5), make_root(3.14159265358979 + a5 - at5)};
         bool j5ok[2] = {true, !same_root(j5r[0], j5r[1])};
+        if (same_root_borderline(j5r[0], j5r[1])) out.status |= kStatusIllConditioned;
 
 TCMP_ROOT_LOOP
         for (int i5 = 0; i5 < 2; ++i5) {
             if (!j5ok[i5]) continue;
             const Root &j5 = j5r[i5];
             // j4: one root (:2404-2408 guards, :3037-3045 formula)
-            const double K = -0.0825 + 0.0825 * j3.c + 0.316 * j3.s;
-            const double U = P.c6 * P.npy + P.npx * P.s6;
-            const double W = (-0.088) * j5.c - j5.c * sn + P.npz * j5.s + j5.c * cn;
-            const double q0 = -1.0 + j3.c + 3.83030303030303 * j3.s;
+            const double K = xadd(xadd(-0.0825, xmul(0.0825, j3.c)), xmul(0.316, j3.s));
+            const double U = xadd(xmul(P.c6, P.npy), xmul(P.npx, P.s6));
+            // (-0.088 cj5) + ((-cj5 npy) sj6) + (npz sj5) + ((cj5 cj6) npx)   (:2406, :3037)
+            const double W = xadd(xadd(xadd(xmul(-0.088, j5.c), xmul(xmul(-j5.c, P.npy), P.s6)), xmul(P.npz, j5.s)),
+                                  xmul(xmul(j5.c, P.c6), P.npx));
+            const double q0 = xadd(xadd(-1.0, j3.c), xmul(3.83030303030303, j3.s));
             const double sK = sign_of(K);
             Root j3u = j3, j4c[2];
             int n4;
+            if (near_threshold(fabs(q0), kBranchThresh) || near_threshold(fabs(U) + fabs(W), kBranchThresh))
+                out.status |= kStatusIllConditioned;
             if (fabs(q0) < kBranchThresh || fabs(U) + fabs(W) < kBranchThresh || fabs(sK) < kBranchThresh) {
                 // Elbow singularity: K = 0, the shoulder centre lies on the forearm (joint-5) axis, so the position
                 // equations say nothing about j4 (U^2 + W^2 = K^2).

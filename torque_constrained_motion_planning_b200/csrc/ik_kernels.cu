@@ -50,8 +50,11 @@ __device__ __forceinline__ void load_pose(int64_t s, int64_t n, int n_free, int 
     prepare_pose(R, __ldg(trans3 + p), __ldg(trans3 + n + p), __ldg(trans3 + 2 * n + p), j6, P);
 }
 
+#ifndef TCMP_IK_MINBLOCKS
+#define TCMP_IK_MINBLOCKS 1
+#endif
 template <bool WRITE_SOLS>
-__global__ void __launch_bounds__(kIkBlock)
+__global__ void __launch_bounds__(kIkBlock, TCMP_IK_MINBLOCKS)
 ik_kernel_compact(int64_t n, int n_free, int free_broadcast, const double *__restrict__ rot9,
                   const double *__restrict__ trans3, const double *__restrict__ free_vals,
                   double *__restrict__ sols_out, int32_t *__restrict__ count_out, uint8_t *__restrict__ status_out) {
@@ -80,10 +83,11 @@ ik_kernel_compact(int64_t n, int n_free, int free_broadcast, const double *__res
             solve_one_t<false>(P, out);
             // elbow singularity: ik_redo_kernel finishes this solve with the complete tree (keeping that tree out of
             // this kernel keeps it at 128 / 150 registers instead of 168)
-            if (out.status & kStatusRedo) out.count = -1;
+            const bool redo = (out.status & kStatusRedo) != 0;
+            if (redo) out.count = 0;
             if (WRITE_SOLS)
                 for (int k = (out.count < 8 ? out.count : 8) * 7; k < 56; ++k) rows[lane * kSolRow + k] = 0.0;
-            count_out[s] = out.count;
+            count_out[s] = redo ? -1 : out.count;
             if (status_out) status_out[s] = (uint8_t)out.status;
         }
         if (WRITE_SOLS) {
