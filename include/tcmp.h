@@ -114,6 +114,24 @@ int tcmp_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const 
                            const void *payload_mass, double payload_scalar, double payload_threshold,
                            void *tau_out, int n_dest, void *const *dest_masks, int64_t dest_offset,
                            void *stream);
+/*
+ * Completion flags of the fused gathers (no host barrier, no collective call, CUDA-graph capturable).  Every rank owns
+ * a sync block (TCMP_PEER_SYNC_BYTES of tcmp_peer_alloc memory, which arrives zeroed; dest_sync[r] = rank r's block as
+ * mapped on this rank, dest_sync[rank] = this rank's own).
+ *   tcmp_peer_signal, enqueued after a scatter kernel (tcmp_rne_batch_scatter, tcmp_edge_feasibility_scatter), stores
+ *     this rank's next epoch into the `arrived[rank]` word of every rank's block: completion of the scatter kernel has
+ *     drained its peer stores, a system-scope fence orders the flag behind them.
+ *   tcmp_peer_wait holds its stream until every rank has published this rank's current epoch (acquire loads) -- from
+ *     then on this rank's gathered buffer holds every rank's results of that step.
+ * Both are one-CTA kernels; run them on a side stream behind an event of the scatter kernel and they cost the step
+ * nothing (3 us in-stream).  Ordering contract for consumers, with the gathered buffer cycling through 3 copies
+ * (distributed.PeerMaskBuffer): reads of step i's copy are enqueued on the stream that carries signal/wait, after
+ * wait(i) and before signal(i + 1); the scatter kernel of step i + 3 is ordered after this rank's wait(i + 1) -- every
+ * peer has then published i + 1, i.e. finished reading step i.
+ */
+#define TCMP_PEER_SYNC_BYTES 128
+int tcmp_peer_signal(int rank, int n_dest, void *const *dest_sync, void *stream);
+int tcmp_peer_wait(void *own_sync, int n_ranks, void *stream);
 /* Peer-shareable device memory (cudaMalloc + CUDA IPC): allocate on the current device and export a 64-byte
  * handle; another process on the same node opens the handle to obtain a pointer valid on ITS current device. */
 #define TCMP_IPC_HANDLE_BYTES 64

@@ -312,8 +312,23 @@ def test_scatter_kernel_single_rank(eng):
         assert np.array_equal(buf.gathered[0].cpu().numpy(), ok_o)
         if mode != "base":
             assert np.abs(tau.cpu().numpy() - tau_o).max() < TOL64
-    # consecutive steps alternate between the two copies of the gathered buffer (read -> next-write ordering)
-    assert seen[0] != seen[1] and seen[0] == seen[2] and seen[1] == seen[3]
+    # completion-flag form: signal + wait ride on the side stream, the copies cycle 0, 1, 2; no host synchronisation
+    # between the step and the read (the read is enqueued on the side stream behind the wait); an empty shard
+    # publishes its epoch too
+    for mode in ["rne", "base", "nov"]:
+        buf._slots.zero_()
+        buf.torque_test(dev(q), dev(qd), dev(qdd), dev(mass), mode=mode, want_tau=False, overlap_gather=True)
+        with torch.cuda.stream(buf.side):
+            got = buf.gathered[0].clone()
+        buf.join()
+        _, ok_o = oracle.torque_test_batch(mode, q, qd, qdd, mass)
+        assert np.array_equal(got.cpu().numpy(), ok_o)
+    buf.torque_test(dev(q[:, :0]), dev(qd[:, :0]), dev(qdd[:, :0]), dev(mass[:0]), want_tau=False, overlap_gather=True)
+    buf.join()
+    torch.cuda.synchronize()
+    seen = seen[:4]
+    # consecutive steps cycle through the three copies of the gathered buffer (read -> next-write ordering)
+    assert len(set(seen[:3])) == 3 and seen[0] == seen[3]
     buf.close()
 
 

@@ -10,7 +10,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtcmp.so")
+# TCMP_LIB selects an experimental build (libtcmp<suffix>.so of build.build(suffix=...)) for A/B scripts; still a
+# libtcmp CUDA library or nothing -- there is no CPU fallback either way
+LIB_PATH = os.environ.get("TCMP_LIB") or os.path.join(_HERE, "libtcmp.so")
 
 OK = 0
 MODE = {"rne": 0, "nov": 1, "dyn": 2, "base": 3}
@@ -38,6 +40,8 @@ SIGNATURES = {
     "tcmp_extend_prefix_model": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _f64, _f64, _f64, _vp, _vp, _vp]),
     "tcmp_rne_batch_scatter": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _i32,
                                       ctypes.POINTER(_vp), _i64, _vp]),
+    "tcmp_peer_signal": (_i32, [_i32, _i32, ctypes.POINTER(_vp), _vp]),
+    "tcmp_peer_wait": (_i32, [_vp, _i32, _vp]),
     "tcmp_peer_alloc": (_i32, [ctypes.POINTER(_vp), _i64, ctypes.c_char_p]),
     "tcmp_peer_free": (_i32, [_vp]),
     "tcmp_peer_open": (_i32, [ctypes.c_char_p, ctypes.POINTER(_vp)]),

@@ -47,6 +47,12 @@ struct MaskDests {
     int64_t offset;
 };
 
+// sync blocks of all ranks as one kernel argument (tcmp_peer_signal)
+struct SyncDests {
+    PeerSync *sync[TCMP_MAX_PEERS];
+    int n_sync, rank;
+};
+
 // Launch bounds: 128-thread CTAs.  Single-buffered, ptxas settles on 128 registers (4 CTAs / SM, no spills); the
 // double-buffered default asks for 3 CTAs / SM (168 registers, no spills).  Capping
 // lower (TCMP_RNE_MIN_BLOCKS=5) trades spills for occupancy -- measured slower, see profiles/.
@@ -89,7 +95,7 @@ rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T
     // and is 16 % slower; prefetch.global of the next rows costs 76 registers and 9 % -- see DESIGN.md 6b.)
     const I stride = (I)(gridDim.x * blockDim.x);
     I i = (I)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (i >= n) return;
+    const bool any = i < n;
     auto load = [&](I at, T (&lq)[7], T (&lv)[7], T (&la)[7], T &lm) {
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
@@ -117,21 +123,23 @@ rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T
             __stcs(feasible_out + at, (uint8_t)within_limits<T>(tau));
         }
     };
-    T qa[7], va[7], aa[7], ma, qb[7], vb[7], ab[7], mb;
-    load(i, qa, va, aa, ma);
-    for (;;) {
-        const I nx = i + stride;
-        const bool more = nx < n;
-        if (more) load(nx, qb, vb, ab, mb);
-        consume(i, qa, va, aa, ma);
-        if (!more) break;
+    if (any) {
+        T qa[7], va[7], aa[7], ma, qb[7], vb[7], ab[7], mb;
+        load(i, qa, va, aa, ma);
+        for (;;) {
+            const I nx = i + stride;
+            const bool more = nx < n;
+            if (more) load(nx, qb, vb, ab, mb);
+            consume(i, qa, va, aa, ma);
+            if (!more) break;
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            qa[j] = qb[j];
-            if constexpr (DYN) { va[j] = vb[j]; aa[j] = ab[j]; }
+            for (int j = 0; j < 7; ++j) {
+                qa[j] = qb[j];
+                if constexpr (DYN) { va[j] = vb[j]; aa[j] = ab[j]; }
+            }
+            ma = mb;
+            i = nx;
         }
-        ma = mb;
-        i = nx;
     }
 }
 #else
@@ -214,7 +222,8 @@ static cudaError_t launch_indexed(int64_t n, const void *q, const void *qd, cons
 template <typename T, bool DYN, bool TOOL, bool WT, bool WM>
 static cudaError_t launch_one(int64_t n, const void *q, const void *qd, const void *qdd, const void *pm,
                               double ps, double pt, void *tau, uint8_t *mask, cudaStream_t st) {
-    return launch_indexed<T, DYN, TOOL, WT, WM, false>(n, q, qd, qdd, pm, ps, pt, tau, mask, MaskDests(), st);
+    MaskDests none = {};
+    return launch_indexed<T, DYN, TOOL, WT, WM, false>(n, q, qd, qdd, pm, ps, pt, tau, mask, none, st);
 }
 
 template <typename T, bool DYN, bool TOOL>
@@ -263,10 +272,54 @@ static cudaError_t launch_scatter_t(int64_t n, const void *q, const void *qd, co
     return launch_indexed<T, DYN, TOOL, false, true, true>(n, q, qd, qdd, pm, ps, pt, tau, nullptr, dests, st);
 }
 
+// ---- completion flags of the fused gathers -----------------------------------------------------------------------
+// Publish: enqueued after a scatter kernel.  Kernel completion has drained that grid's peer stores, so one thread
+// fences and stores this rank's new epoch into the `arrived[rank]` word of every rank's sync block.  (Publishing from
+// inside the scatter kernel -- a system-scope fence + ticket at the end of each CTA, flags written by the CTA that
+// draws the last ticket -- was built and measured: 21-27 us per launch at 4 grid waves, 6-8 us at one, because every
+// retiring CTA then waits for its stores to be acknowledged by a saturated memory system; this kernel costs 3 us
+// in-stream and nothing on a side stream.  profiles/r02/scatter_signal_variants_n2.log)
+__global__ void peer_signal_kernel(SyncDests d) {
+    PeerSync *own = d.sync[d.rank];
+    const unsigned long long e = own->epoch + 1;
+    own->epoch = e;
+    __threadfence_system();
+    for (int r = 0; r < d.n_sync; ++r) *reinterpret_cast<volatile unsigned long long *>(&d.sync[r]->arrived[d.rank]) = e;
+}
+
+// Consumer side: lane r waits until rank r has published an epoch >= this rank's own (every rank runs the same
+// sequence of scatter steps, so epochs line up); acquire loads at system scope, back-off while spinning.
+__global__ void peer_wait_kernel(PeerSync *own, int world) {
+    const unsigned long long e = own->epoch;
+    if ((int)threadIdx.x < world) {
+        const unsigned long long *flag = &own->arrived[threadIdx.x];
+        unsigned long long v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            if (v >= e) break;
+            __nanosleep(200);
+        }
+    }
+}
+
+cudaError_t launch_peer_signal(int rank, int n_dest, void *const *dest_sync, cudaStream_t st) {
+    SyncDests d = {};
+    d.n_sync = n_dest;
+    d.rank = rank;
+    for (int i = 0; i < n_dest; ++i) d.sync[i] = (PeerSync *)dest_sync[i];
+    peer_signal_kernel<<<1, 1, 0, st>>>(d);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_wait(void *own_sync, int world, cudaStream_t st) {
+    peer_wait_kernel<<<1, 32, 0, st>>>((PeerSync *)own_sync, world);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
                                      const void *pm, double ps, double pt, void *tau, int n_dest,
                                      void *const *dest_masks, int64_t dest_offset, cudaStream_t st) {
-    MaskDests d;
+    MaskDests d = {};
     d.n = n_dest;
     d.offset = dest_offset;
     for (int i = 0; i < TCMP_MAX_PEERS; ++i) d.p[i] = i < n_dest ? (uint8_t *)dest_masks[i] : nullptr;

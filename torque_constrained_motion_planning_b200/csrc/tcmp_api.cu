@@ -221,10 +221,26 @@ int tcmp_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const 
     return TCMP_OK;
 }
 
+int tcmp_peer_signal(int rank, int n_dest, void *const *dest_sync, void *stream) {
+    if (n_dest < 1 || n_dest > TCMP_MAX_PEERS || !dest_sync || rank < 0 || rank >= n_dest)
+        return fail(TCMP_ERR_INVALID_ARG, "bad sync list");
+    for (int i = 0; i < n_dest; ++i)
+        if (!dest_sync[i]) return fail(TCMP_ERR_INVALID_ARG, "dest_sync[%d] is NULL", i);
+    TCMP_CUDA(launch_peer_signal(rank, n_dest, dest_sync, (cudaStream_t)stream));
+    return TCMP_OK;
+}
+
+int tcmp_peer_wait(void *own_sync, int n_ranks, void *stream) {
+    if (!own_sync || n_ranks < 1 || n_ranks > TCMP_MAX_PEERS) return fail(TCMP_ERR_INVALID_ARG, "bad sync block");
+    TCMP_CUDA(launch_peer_wait(own_sync, n_ranks, (cudaStream_t)stream));
+    return TCMP_OK;
+}
+
 int tcmp_peer_alloc(void **dev_ptr, int64_t bytes, unsigned char *handle_out) {
     if (!dev_ptr || bytes <= 0 || !handle_out) return fail(TCMP_ERR_INVALID_ARG, "bad peer alloc");
     static_assert(sizeof(cudaIpcMemHandle_t) == TCMP_IPC_HANDLE_BYTES, "IPC handle size");
     TCMP_CUDA(cudaMalloc(dev_ptr, (size_t)bytes));
+    TCMP_CUDA(cudaMemset(*dev_ptr, 0, (size_t)bytes));   // sync blocks (TCMP_PEER_SYNC_BYTES) start at epoch 0
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
     if (e != cudaSuccess) {

@@ -43,10 +43,23 @@ cudaError_t launch_rne_batch_model(const tcmp_model &model, int mode, int dtype,
 void default_model_desc(tcmp_model *out);
 const char *model_desc_problem(const tcmp_model &model);
 
+// Per-rank sync block of the fused gathers (TCMP_PEER_SYNC_BYTES, allocated with tcmp_peer_alloc, zeroed once):
+// arrived[r] = last epoch rank r has published here (written by rank r's kernels over NVLink); epoch / ticket are
+// this rank's own.
+struct PeerSync {
+    unsigned long long arrived[TCMP_MAX_PEERS];
+    unsigned long long epoch;
+    unsigned int ticket;
+    unsigned int pad[13];
+};
+static_assert(sizeof(PeerSync) == TCMP_PEER_SYNC_BYTES, "tcmp.h: TCMP_PEER_SYNC_BYTES");
+
 cudaError_t launch_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
                                      const void *payload_mass, double payload_scalar, double payload_threshold,
                                      void *tau_out, int n_dest, void *const *dest_masks, int64_t dest_offset,
                                      cudaStream_t st);
+cudaError_t launch_peer_signal(int rank, int n_dest, void *const *dest_sync, cudaStream_t st);
+cudaError_t launch_peer_wait(void *own_sync, int world, cudaStream_t st);
 
 cudaError_t launch_edge_feasibility(int mode, int dtype, int64_t n_edges, int n_waypoints, const void *qa,
                                     const void *qb, double payload_scalar, double payload_threshold,

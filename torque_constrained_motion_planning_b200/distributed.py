@@ -162,17 +162,25 @@ class PeerMaskBuffer:
     CUDA IPC), the 64-byte handles are exchanged once through torch.distributed, and peers are mapped with
     tcmp_peer_open.  After ``torque_test`` + a stream sync + ``barrier()`` every rank holds every mask.
 
-    Ordering protocol.  The buffer has ``SLOTS`` = 2 copies and step i writes copy i % 2, so the one ``barrier()`` per
-    step orders both directions: (write -> read) every rank's stores of step i land before anyone reads copy i % 2;
-    (read -> next write) copy i % 2 is next written by step i + 2, which a peer can only launch after it left
-    barrier i + 1, i.e. after this rank ENTERED barrier i + 1 -- so a consumer must finish reading ``gathered`` of
-    step i before it calls ``barrier()`` for step i + 1 (enqueue the reads on the current stream: ``barrier``
-    synchronises the device first).  With a single copy a fast rank's step i + 1 could overwrite row r of a slower
-    rank's buffer while that rank was still reading step i."""
+    Completion and ordering, without a host barrier or a collective call (``overlap_gather=True``).  After every
+    scatter kernel a side stream runs ``signal()`` (tcmp_peer_signal: this rank publishes the step's epoch into every
+    rank's sync block) and ``wait()`` (tcmp_peer_wait: holds the side stream until every rank has published it); both
+    ride under the NEXT step's kernel on the producer stream, so the gather's completion costs the step nothing.  The
+    buffer cycles through ``SLOTS`` = 3 copies and the scatter kernel of step i + 3 is ordered behind this rank's
+    wait(i + 1).  Contract for a consumer of step i's masks: enqueue the reads on ``side`` right after the step (they
+    then run after wait(i) and before signal(i + 1)); a peer can only overwrite copy i % 3 in step i + 3, i.e. after it
+    has seen every rank publish i + 1, which this rank does after those reads.  ``join()`` makes the current stream
+    wait for the last wait.  Everything is plain kernel launches and events: CUDA-graph capturable (call ``reset()``
+    before a capture so no event recorded outside the capture is waited on inside).
+
+    ``barrier()`` (stream sync + torch.distributed barrier) remains for callers that synchronise on the host: with one
+    barrier per step, step i + 1's writes go to another copy than step i's, and a copy is written again only two
+    barriers later, so readers of step i must be done before they enter the barrier of step i + 1.  (With a single
+    copy a fast rank's next step could overwrite a row a slower rank was still reading: ADVICE r01.)"""
 
     itemsize = 1
     typestr = "|u1"
-    SLOTS = 2
+    SLOTS = 3
 
     def __init__(self, n_per_rank: int, group=None):
         import ctypes
@@ -208,6 +216,27 @@ class PeerMaskBuffer:
                 self._peers.append(p)
                 ptrs[r] = p.value
         self._ptrs = ptrs
+        # completion flags of the fused gather: one TCMP_PEER_SYNC_BYTES block per rank, peers mapped like the buffers
+        self._sync_own = ctypes.c_void_p()
+        shandle = ctypes.create_string_buffer(64)
+        self._check(self._lib.tcmp_peer_alloc(ctypes.byref(self._sync_own), 128, shandle))
+        smine = torch.tensor(list(shandle.raw), dtype=torch.uint8, device=dev)
+        sptrs = (ctypes.c_void_p * self.world)()
+        if self.world > 1:
+            sall = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
+            _dist().all_gather_into_tensor(sall, smine, group=group)
+            sall = sall.cpu().numpy()
+        for r in range(self.world):
+            if r == self.rank:
+                sptrs[r] = self._sync_own.value
+            else:
+                p = ctypes.c_void_p()
+                self._check(self._lib.tcmp_peer_open(bytes(sall[r].tobytes()), ctypes.byref(p)))
+                self._peers.append(p)
+                sptrs[r] = p.value
+        self._sync_ptrs = sptrs
+        self.side = torch.cuda.Stream(device=dev)     # carries signal / wait (and a consumer's reads)
+        self._done = {}                               # step -> event recorded on `side` after wait(step)
         self._slots = torch.as_tensor(_DevArray(self._own.value, self.SLOTS * self.n * self.world, self.typestr),
                                       device=dev).view(self.SLOTS, self.world, self.n)
         self.gathered = self._slots[0]
@@ -220,9 +249,10 @@ class PeerMaskBuffer:
         return (slot * self.world + self.rank) * self.n
 
     def torque_test(self, q, qd=None, qdd=None, payload_mass=0.0, mode="rne", payload_threshold=0.01,
-                    want_tau=True, out_tau=None):
+                    want_tau=True, out_tau=None, overlap_gather=False):
         """Evaluate this rank's block (q/qd/qdd [7][n] CUDA tensors) and store its mask into row ``rank`` of the
-        gathered buffer on EVERY rank.  Returns tau [7][n] (or None)."""
+        gathered buffer on EVERY rank.  Returns tau [7][n] (or None).  ``overlap_gather=True``: completion flags on
+        the side stream as described in the class docstring (then use ``join()``, not ``barrier()``)."""
         import torch
         from ._lib import DTYPE, MODE
         n = int(q.shape[1])
@@ -231,10 +261,60 @@ class PeerMaskBuffer:
         tau = (out_tau if out_tau is not None else torch.empty((7, n), dtype=torch.float64, device=q.device)) \
             if want_tau else None
         ptr = lambda t: None if t is None else int(t.data_ptr())
+        if overlap_gather:
+            self._before_step()
         self._check(self._lib.tcmp_rne_batch_scatter(
             MODE[mode], DTYPE["f64"], n, ptr(q), ptr(qd), ptr(qdd), ptr(pm), scalar, float(payload_threshold),
             ptr(tau), self.world, self._ptrs, self._next_offset(), int(torch.cuda.current_stream().cuda_stream)))
+        if overlap_gather:
+            self._after_step()
         return tau
+
+    def _before_step(self):
+        """The coming step (index self._step) overwrites the copy of step - SLOTS: order it behind wait(step - 2)."""
+        import torch
+        ev = self._done.get(self._step - (self.SLOTS - 1))
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _after_step(self):
+        """signal + wait of the step just launched (self._step - 1) on the side stream."""
+        import torch
+        step = self._step - 1
+        launched = torch.cuda.Event()
+        launched.record(torch.cuda.current_stream())
+        self.side.wait_event(launched)
+        with torch.cuda.stream(self.side):
+            self.signal()
+            self.wait()
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self._done[step] = done
+        self._done.pop(step - self.SLOTS, None)
+
+    def join(self):
+        """Current stream waits until the last step's gather is complete on this rank."""
+        import torch
+        if self._done:
+            torch.cuda.current_stream().wait_event(self._done[max(self._done)])
+
+    def reset(self):
+        """Forget the recorded completion events (host side only; synchronise first).  Call before capturing steps into
+        a CUDA graph and after the capture: events of one regime must not be waited on in the other."""
+        self._done = {}
+
+    def signal(self):
+        """Publish this rank's completion after a scatter kernel that does not signal itself (tcmp_peer_signal)."""
+        import torch
+        self._check(self._lib.tcmp_peer_signal(self.rank, self.world, self._sync_ptrs,
+                                               int(torch.cuda.current_stream().cuda_stream)))
+
+    def wait(self):
+        """Device-side wait (tcmp_peer_wait, one tiny kernel on the current stream): returns at once on the host; work
+        enqueued after it runs when every rank has published this rank's current epoch, i.e. ``gathered`` is
+        complete.  No host barrier, no collective call; CUDA-graph capturable."""
+        import torch
+        self._check(self._lib.tcmp_peer_wait(self._sync_own, self.world, int(torch.cuda.current_stream().cuda_stream)))
 
     def barrier(self):
         """Order every rank's peer stores before anyone reads ``gathered``."""
@@ -247,6 +327,9 @@ class PeerMaskBuffer:
         for p in self._peers:
             self._lib.tcmp_peer_close(p)
         self._peers = []
+        if self._sync_own:
+            self._lib.tcmp_peer_free(self._sync_own)
+            self._sync_own = None
         if self._own:
             self.gathered = self._slots = None
             self._lib.tcmp_peer_free(self._own)
@@ -262,14 +345,18 @@ class PeerIndexBuffer(PeerMaskBuffer):
     typestr = "<i4"
 
     def edge_feasibility(self, qa, qb, n_waypoints=64, payload_mass=0.0, mode="rne", payload_threshold=0.01,
-                         static_only=False):
+                         static_only=False, overlap_gather=False):
         """Evaluate this rank's block of edges (qa/qb [7][n] CUDA fp64 tensors); row ``rank`` of ``gathered`` on
         every rank receives the first-failure indices."""
         import torch
         from ._lib import MODE
         n = int(qa.shape[1])
         assert n <= self.n
+        if overlap_gather:
+            self._before_step()
         self._check(self._lib.tcmp_edge_feasibility_scatter(
             MODE[mode], n, int(n_waypoints), int(qa.data_ptr()), int(qb.data_ptr()), float(payload_mass),
             float(payload_threshold), int(static_only), self.world, self._ptrs, self._next_offset(),
             int(torch.cuda.current_stream().cuda_stream)))
+        if overlap_gather:
+            self._after_step()
