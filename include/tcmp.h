@@ -130,6 +130,11 @@ int tcmp_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const 
  * peer has then published i + 1, i.e. finished reading step i.
  */
 #define TCMP_PEER_SYNC_BYTES 128
+/* The gather as its own small kernel: copy `bytes` of a result block this rank has produced (device pointer src) into
+ * dests[d] + dest_offset for every d < n_dest.  On a side stream behind the producing kernel (tcmp_rne_batch,
+ * tcmp_edge_feasibility, tcmp_ik_batch counts ...) it overlaps the next step; the alternative to the fused epilogues
+ * for results the kernels do not scatter themselves, and measured against them in profiles/r02/. */
+int tcmp_peer_push(const void *src, int64_t bytes, int n_dest, void *const *dests, int64_t dest_offset, void *stream);
 int tcmp_peer_signal(int rank, int n_dest, void *const *dest_sync, void *stream);
 int tcmp_peer_wait(void *own_sync, int n_ranks, void *stream);
 /* Peer-shareable device memory (cudaMalloc + CUDA IPC): allocate on the current device and export a 64-byte

@@ -5,8 +5,9 @@
   A  scatter kernel only (peer stores, no completion flags)               -- producer-only, as round 1 timed it
   F  A + tcmp_peer_signal + tcmp_peer_wait in the same stream after every step
   G  A + signal / wait on a side stream under the next step's kernel (PeerMaskBuffer overlap_gather=True)
+  H  plain kernel, then on the side stream tcmp_peer_push (copy the local mask block to every rank) + signal / wait
 Each: 200 steps captured in one CUDA graph, replayed 20x after a barrier, max over ranks.
-(The in-kernel completion-flag tail measured in profiles/r02/scatter_signal_variants_n2.log was removed.)
+(The in-kernel completion-flag tail measured in profiles/r02/scatter_signal_variants.log was removed.)
 """
 import os
 import sys
@@ -44,6 +45,15 @@ def var_f(i):
 
 def var_g(i):
     peer.torque_test(*sets[i % 4], mode="rne", out_tau=out_tau, overlap_gather=True)
+
+
+masks2 = [torch.empty((N_STATES,), dtype=torch.uint8, device=dev) for _ in range(2)]
+
+
+def var_h(i):
+    peer.before_step()
+    _, ok = engine.torque_test_batch(*sets[i % 4], mode="rne", out_tau=out_tau, out_mask=masks2[i % 2])
+    peer.push(ok)
 
 
 def var_e(i):
@@ -85,7 +95,7 @@ def timeit(g, reps=20, k=200):
 
 res = {}
 for name, fn in (("E_plain", var_e), ("A_scatter", var_a), ("F_signal_wait_in_stream", var_f),
-                 ("G_signal_wait_side_stream", var_g), ("E_plain_again", var_e)):
+                 ("G_signal_wait_side_stream", var_g), ("H_unfused_push_side_stream", var_h), ("E_plain_again", var_e)):
     res[name] = timeit(capture(fn))
 if rank == 0:
     print(json.dumps({"world": world, "lib": os.path.basename(os.environ.get("TCMP_LIB", "libtcmp.so")), "us_per_step": res}))

@@ -53,6 +53,18 @@ struct SyncDests {
     int n_sync, rank;
 };
 
+// Scatter epilogue: the 32 lanes of a warp store 32 consecutive mask bytes into every rank's gathered buffer -- one
+// 32-byte sector request per peer per warp round.  (Packing the verdicts with a ballot into 16-byte vector stores, one
+// store instruction for all peers, was measured at N = 8: 54.1 us per step against 52.7 us for these byte stores -- the
+// hardware already coalesces the byte lanes, the vector form only doubles the request count.)
+template <typename I>
+__device__ __forceinline__ void scatter_mask(const MaskDests &dests, I at, bool ok) {
+    const uint8_t m = (uint8_t)ok;
+#pragma unroll
+    for (int d = 0; d < TCMP_MAX_PEERS; ++d)   // unrolled: constant indices keep `dests` in param space
+        if (d < dests.n) dests.p[d][dests.offset + at] = m;
+}
+
 // Launch bounds: 128-thread CTAs.  Single-buffered, ptxas settles on 128 registers (4 CTAs / SM, no spills); the
 // double-buffered default asks for 3 CTAs / SM (168 registers, no spills).  Capping
 // lower (TCMP_RNE_MIN_BLOCKS=5) trades spills for occupancy -- measured slower, see profiles/.
@@ -70,7 +82,7 @@ template <typename T, typename I, bool DYN, bool TOOL, bool WRITE_TAU, bool WRIT
 __global__ void __launch_bounds__(TCMP_RNE_BOUNDS)
 rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T *__restrict__ qdd,
                  const T *__restrict__ payload_mass, T payload_scalar, T payload_threshold,
-                 T *__restrict__ tau_out, uint8_t *__restrict__ feasible_out, MaskDests dests) {
+                 T *__restrict__ tau_out, uint8_t *__restrict__ feasible_out, const __grid_constant__ MaskDests dests) {
     // dynamic fp64 kernels only: the static (nov) kernel is HBM-leaning and measured 1.4 % slower with the staging
     constexpr bool kTable = TCMP_TABLE_SINCOS && sizeof(T) == 8 && DYN;
     __shared__ SinCos tab[kTable ? kSinCosTableSize : 1];
@@ -115,10 +127,7 @@ rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T
             for (int j = 0; j < 7; ++j) __stcs(tau_out + j * n + at, tau[j]);
         }
         if constexpr (SCATTER) {
-            const uint8_t m = (uint8_t)within_limits<T>(tau);
-#pragma unroll
-            for (int d = 0; d < TCMP_MAX_PEERS; ++d)   // unrolled: constant indices keep `dests` in param space
-                if (d < dests.n) dests.p[d][dests.offset + at] = m;
+            scatter_mask<I>(dests, at, within_limits<T>(tau));
         } else if constexpr (WRITE_MASK) {
             __stcs(feasible_out + at, (uint8_t)within_limits<T>(tau));
         }
@@ -166,10 +175,7 @@ rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T
             for (int j = 0; j < 7; ++j) __stcs(tau_out + j * n + i, tau[j]);
         }
         if constexpr (SCATTER) {
-            const uint8_t m = (uint8_t)within_limits<T>(tau);
-#pragma unroll
-            for (int d = 0; d < TCMP_MAX_PEERS; ++d)   // unrolled: constant indices keep `dests` in param space
-                if (d < dests.n) dests.p[d][dests.offset + i] = m;
+            scatter_mask<I>(dests, i, within_limits<T>(tau));
         } else if constexpr (WRITE_MASK) {
             __stcs(feasible_out + i, (uint8_t)within_limits<T>(tau));
         }
@@ -278,7 +284,7 @@ static cudaError_t launch_scatter_t(int64_t n, const void *q, const void *qd, co
 // inside the scatter kernel -- a system-scope fence + ticket at the end of each CTA, flags written by the CTA that
 // draws the last ticket -- was built and measured: 21-27 us per launch at 4 grid waves, 6-8 us at one, because every
 // retiring CTA then waits for its stores to be acknowledged by a saturated memory system; this kernel costs 3 us
-// in-stream and nothing on a side stream.  profiles/r02/scatter_signal_variants_n2.log)
+// in-stream and nothing on a side stream.  profiles/r02/scatter_signal_variants.log)
 __global__ void peer_signal_kernel(SyncDests d) {
     PeerSync *own = d.sync[d.rank];
     const unsigned long long e = own->epoch + 1;
@@ -300,6 +306,56 @@ __global__ void peer_wait_kernel(PeerSync *own, int world) {
             __nanosleep(200);
         }
     }
+}
+
+// Stand-alone gather step: copy `bytes` of this rank's result block into every rank's gathered buffer at dest_offset
+// (a few CTAs, 16-byte loads and stores when everything is 16-byte aligned).  Run on the side stream behind the
+// producing kernel it rides under the NEXT step's kernel -- the alternative to the fused peer-store epilogue.
+__global__ void __launch_bounds__(256)
+peer_push_kernel(const uint8_t *__restrict__ src, int64_t bytes, MaskDests d, int vec) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const int64_t nv = bytes / 16;
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+        for (int64_t i = tid; i < nv; i += stride) {
+            const uint4 v = __ldg(s4 + i);
+#pragma unroll
+            for (int r = 0; r < TCMP_MAX_PEERS; ++r)
+                if (r < d.n) reinterpret_cast<uint4 *>(d.p[r] + d.offset)[i] = v;
+        }
+        for (int64_t i = nv * 16 + tid; i < bytes; i += stride) {
+            const uint8_t v = src[i];
+#pragma unroll
+            for (int r = 0; r < TCMP_MAX_PEERS; ++r)
+                if (r < d.n) d.p[r][d.offset + i] = v;
+        }
+    } else {
+        for (int64_t i = tid; i < bytes; i += stride) {
+            const uint8_t v = src[i];
+#pragma unroll
+            for (int r = 0; r < TCMP_MAX_PEERS; ++r)
+                if (r < d.n) d.p[r][d.offset + i] = v;
+        }
+    }
+}
+
+cudaError_t launch_peer_push(const void *src, int64_t bytes, int n_dest, void *const *dests, int64_t dest_offset,
+                             cudaStream_t st) {
+    MaskDests d = {};
+    d.n = n_dest;
+    d.offset = dest_offset;
+    int vec = ((uintptr_t)src % 16 == 0);
+    for (int i = 0; i < n_dest; ++i) {
+        d.p[i] = (uint8_t *)dests[i];
+        if (((uintptr_t)dests[i] + (uintptr_t)dest_offset) % 16 != 0) vec = 0;
+    }
+    const int64_t units = vec ? bytes / 16 : bytes;
+    int grid = (int)((units + 255) / 256);
+    if (grid > 32) grid = 32;     // a side-stream copy: leave the SMs to the torque kernel it overlaps
+    if (grid < 1) grid = 1;
+    peer_push_kernel<<<grid, 256, 0, st>>>((const uint8_t *)src, bytes, d, vec);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_peer_signal(int rank, int n_dest, void *const *dest_sync, cudaStream_t st) {

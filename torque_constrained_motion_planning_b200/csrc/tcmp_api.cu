@@ -221,6 +221,17 @@ int tcmp_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const 
     return TCMP_OK;
 }
 
+int tcmp_peer_push(const void *src, int64_t bytes, int n_dest, void *const *dests, int64_t dest_offset, void *stream) {
+    if (bytes < 0 || n_dest < 1 || n_dest > TCMP_MAX_PEERS || !dests || dest_offset < 0)
+        return fail(TCMP_ERR_INVALID_ARG, "bad push arguments");
+    for (int i = 0; i < n_dest; ++i)
+        if (!dests[i]) return fail(TCMP_ERR_INVALID_ARG, "dests[%d] is NULL", i);
+    if (bytes == 0) return TCMP_OK;
+    if (!src) return fail(TCMP_ERR_INVALID_ARG, "src is NULL");
+    TCMP_CUDA(launch_peer_push(src, bytes, n_dest, dests, dest_offset, (cudaStream_t)stream));
+    return TCMP_OK;
+}
+
 int tcmp_peer_signal(int rank, int n_dest, void *const *dest_sync, void *stream) {
     if (n_dest < 1 || n_dest > TCMP_MAX_PEERS || !dest_sync || rank < 0 || rank >= n_dest)
         return fail(TCMP_ERR_INVALID_ARG, "bad sync list");

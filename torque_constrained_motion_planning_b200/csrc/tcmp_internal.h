@@ -59,6 +59,8 @@ cudaError_t launch_rne_batch_scatter(int mode, int dtype, int64_t n, const void 
                                      void *tau_out, int n_dest, void *const *dest_masks, int64_t dest_offset,
                                      cudaStream_t st);
 cudaError_t launch_peer_signal(int rank, int n_dest, void *const *dest_sync, cudaStream_t st);
+cudaError_t launch_peer_push(const void *src, int64_t bytes, int n_dest, void *const *dests, int64_t dest_offset,
+                             cudaStream_t st);
 cudaError_t launch_peer_wait(void *own_sync, int world, cudaStream_t st);
 
 cudaError_t launch_edge_feasibility(int mode, int dtype, int64_t n_edges, int n_waypoints, const void *qa,

@@ -262,7 +262,7 @@ class PeerMaskBuffer:
             if want_tau else None
         ptr = lambda t: None if t is None else int(t.data_ptr())
         if overlap_gather:
-            self._before_step()
+            self.before_step()
         self._check(self._lib.tcmp_rne_batch_scatter(
             MODE[mode], DTYPE["f64"], n, ptr(q), ptr(qd), ptr(qdd), ptr(pm), scalar, float(payload_threshold),
             ptr(tau), self.world, self._ptrs, self._next_offset(), int(torch.cuda.current_stream().cuda_stream)))
@@ -270,7 +270,7 @@ class PeerMaskBuffer:
             self._after_step()
         return tau
 
-    def _before_step(self):
+    def before_step(self):
         """The coming step (index self._step) overwrites the copy of step - SLOTS: order it behind wait(step - 2)."""
         import torch
         ev = self._done.get(self._step - (self.SLOTS - 1))
@@ -302,6 +302,28 @@ class PeerMaskBuffer:
         """Forget the recorded completion events (host side only; synchronise first).  Call before capturing steps into
         a CUDA graph and after the capture: events of one regime must not be waited on in the other."""
         self._done = {}
+
+    def push(self, local):
+        """The unfused form of a step: ``local`` (this rank's result block, a CUDA tensor of n * itemsize bytes produced
+        on the current stream) is copied into row ``rank`` of every rank's gathered buffer by tcmp_peer_push on the
+        side stream, followed by signal / wait -- all under the next step's kernel.  The caller alternates ``local``
+        between two buffers and calls ``before_step()`` ahead of each producing kernel (it orders the kernel behind
+        the wait of two steps ago, by when the push that read this buffer has finished)."""
+        import torch
+        off = self._next_offset() * self.itemsize
+        launched = torch.cuda.Event()
+        launched.record(torch.cuda.current_stream())
+        self.side.wait_event(launched)
+        with torch.cuda.stream(self.side):
+            self._check(self._lib.tcmp_peer_push(int(local.data_ptr()), int(local.numel() * local.element_size()),
+                                                 self.world, self._ptrs, off, int(self.side.cuda_stream)))
+            self.signal()
+            self.wait()
+            done = torch.cuda.Event()
+            done.record(self.side)
+        step = self._step - 1
+        self._done[step] = done
+        self._done.pop(step - self.SLOTS, None)
 
     def signal(self):
         """Publish this rank's completion after a scatter kernel that does not signal itself (tcmp_peer_signal)."""
@@ -353,7 +375,7 @@ class PeerIndexBuffer(PeerMaskBuffer):
         n = int(qa.shape[1])
         assert n <= self.n
         if overlap_gather:
-            self._before_step()
+            self.before_step()
         self._check(self._lib.tcmp_edge_feasibility_scatter(
             MODE[mode], n, int(n_waypoints), int(qa.data_ptr()), int(qb.data_ptr()), float(payload_mass),
             float(payload_threshold), int(static_only), self.world, self._ptrs, self._next_offset(),
