@@ -166,8 +166,11 @@ def cpu_baseline_run(n_sample, reps, nthreads=0):
     return n_sample * reps / dt, nthreads, dt
 
 
-FP64_INSTR_PER_STATE = 669.0          # 419 DFMA + 180 DMUL + 70 DADD in K1's loop body (SASS)
-EXEC_FLOPS_PER_STATE = 2 * 419.0 + 180.0 + 70.0
+# What K1 EXECUTES per state on the FP64 pipe: 317 DFMA + 162 DMUL + 70 DADD + 7 DSETP thread instructions, from the
+# source page of the committed ncu capture (profiles/r02/k1_executed_instruction_mix.txt).  Round 1 quoted 669, the
+# STATIC count of the kernel text, which includes the never-taken libm sincos fallback.
+FP64_INSTR_PER_STATE = 556.0
+EXEC_FLOPS_PER_STATE = 2 * 317.0 + 162.0 + 70.0
 
 
 def sample_edges(n, seed):

@@ -89,6 +89,7 @@ rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T
     if constexpr (kTable) {
         // constant data, no dependence on earlier grids: staged BEFORE the programmatic-launch wait below, so it
         // overlaps the previous launch's tail
+        // (cp.async staging overlapped with the first state's loads was measured: no change, 22.40 vs 22.45 G states/s)
         for (int t = threadIdx.x; t < kSinCosTableSize; t += blockDim.x) tab[t] = kSinCosTable[t];
         __syncthreads();
     }
