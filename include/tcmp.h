@@ -221,6 +221,11 @@ int tcmp_ik_batch(int64_t n, const double *rot9, const double *trans3, const dou
  * closest_inverse_kinematics ikfast.py:172-188) or the Euclidean norm (ik_utils.select_solution :43-52).
  *   best_q [7][n], best_cost [n] (+inf when no solution survives), n_valid [n] = surviving solutions.
  * Ties keep the first solution in (free value, solver order).
+ * NOT the reference's order of operations: the reference takes the nearest IN-LIMIT solution first
+ * (closest_inverse_kinematics) and then fails the whole grasp if that single configuration exceeds the torque limits
+ * (panda_primitives.py:263), whereas this call picks the nearest solution among those that ALSO pass the torque test --
+ * it can succeed where the reference returns None.  For the reference's semantics call it with TCMP_MODE_BASE (limit
+ * filter + nearest only) and run tcmp_rne_batch on best_q, which is what panda_primitives.planner_fn_force_aware does.
  */
 int tcmp_ik_select(int64_t n, const double *rot9, const double *trans3, const double *free_vals, int n_free,
                    int free_broadcast, const double *q_ref, int ref_broadcast, const double *q_lo_host,

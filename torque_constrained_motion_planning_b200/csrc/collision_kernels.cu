@@ -17,6 +17,13 @@
 
 namespace tcmp {
 
+// (sin, cos)(i pi / 512) for the table-driven sincos of the static torque tests (panda_model.cuh sincos6_table<GLOBAL>):
+// read in place through the read-only cache -- this kernel's shared memory is spoken for, and its torque tests are
+// too few per CTA to pay for staging 16 KB.  Own copy per translation unit (no relocatable device code in the build).
+static __device__ const SinCos kExtSinCosTable[kSinCosTableSize] = {
+#include "sincos_table.inc"
+};
+
 struct Scene {
     int n_obs;
     int kind[TCMP_MAX_OBSTACLES];            // 0 = box, 1 = sphere
@@ -129,7 +136,12 @@ extend_prefix_kernel(int64_t n_edges, const double *__restrict__ q1, const doubl
             nrm2 = __dadd_rn(nrm2, __dmul_rn(d, d));
         }
         // steps = int(np.linalg.norm(., ord=2)) (utils.py:3074); the sequence has steps + 1 configurations
-        const int N = (int)sqrt(nrm2) + 1;
+        // A non-finite norm (NaN / inf end point) has no step count: report 0 configurations, safe prefix 0, so the
+        // host never truncates a sequence with it (the cast of a NaN to int is undefined); a huge finite norm is
+        // clamped for the same reason.
+        const double nrm = sqrt(nrm2);
+        const bool sane = nrm == nrm && nrm < 1.0e6;
+        const int N = sane ? (int)nrm + 1 : 0;
         int prefix = N;
         for (int base = 0; base < N; base += 32) {
             const int k = base + lane;
@@ -148,7 +160,7 @@ extend_prefix_kernel(int64_t n_edges, const double *__restrict__ q1, const doubl
             if (!bad && check_torque) {   // torque only for collision-free configurations (rrt_star.py:92-96)
                 double tau[7];
                 const double z[7] = {0, 0, 0, 0, 0, 0, 0};
-                rne_core<double, false, TOOL, P>(q, z, z, mp_inertial, mp_tool, tau, prm);
+                rne_core_table<false, TOOL, P, true>(q, z, z, mp_inertial, mp_tool, tau, kExtSinCosTable, prm);   // table read in place (__ldg)
                 bad = !limits_ok<double, P>(tau, prm);
             }
             const unsigned fails = __ballot_sync(0xffffffffu, active && bad);

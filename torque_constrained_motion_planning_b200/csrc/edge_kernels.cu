@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(128)
 edge_kernel(int64_t n_edges, int W, double interval, double step, const T *__restrict__ qa,
             const T *__restrict__ qb, T mass, T payload_threshold, int32_t *__restrict__ first_fail,
             IndexDests dests, const __grid_constant__ P prm) {
-    // compiled-in Panda, fp64, dynamic: the same table-driven sincos as K1 (14 instead of 21 FP64 instr / angle)
-    constexpr bool kTable = sizeof(T) == 8 && DYN && kIsConst<P>;
+    // fp64, dynamic: the same table-driven sincos as K1 (14 instead of 21 FP64 instr / angle)
+    constexpr bool kTable = sizeof(T) == 8 && DYN;
     __shared__ SinCos tab[kTable ? kSinCosTableSize : 1];
     if constexpr (kTable) {
         for (int t = threadIdx.x; t < kSinCosTableSize; t += blockDim.x) tab[t] = kEdgeSinCosTable[t];
@@ -80,7 +80,7 @@ edge_kernel(int64_t n_edges, int W, double interval, double step, const T *__res
                     as[j] = A[j] * pa;
                 }
             }
-            if constexpr (kTable) rne_core_table<DYN, TOOL>(qs, vs, as, mp_inertial, mp_tool, tau, tab);
+            if constexpr (kTable) rne_core_table<DYN, TOOL, P>(qs, vs, as, mp_inertial, mp_tool, tau, tab, prm);
             else rne_core<T, DYN, TOOL, P>(qs, vs, as, mp_inertial, mp_tool, tau, prm);
             const unsigned fails = __ballot_sync(0xffffffffu, active && !limits_ok<T, P>(tau, prm));
             if (fails) {
@@ -106,6 +106,12 @@ traj_kernel(int n_seg, int S, double interval, double step, const double *__rest
             T payload_threshold, T *__restrict__ q_out, T *__restrict__ qd_out, T *__restrict__ qdd_out,
             T *__restrict__ tau_out, uint8_t *__restrict__ feasible_out, int32_t *__restrict__ first_fail,
             const __grid_constant__ P prm) {
+    constexpr bool kTable = sizeof(T) == 8 && DYN;    // table-driven sincos, as in K1 and the edge kernel
+    __shared__ SinCos tab[kTable ? kSinCosTableSize : 1];
+    if constexpr (kTable) {
+        for (int t = threadIdx.x; t < kSinCosTableSize; t += blockDim.x) tab[t] = kEdgeSinCosTable[t];
+        __syncthreads();
+    }
     const int64_t n = (int64_t)n_seg * S;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const T mp_inertial = TOOL ? T(0) : (mass > payload_threshold ? mass : T(0));
@@ -122,7 +128,8 @@ traj_kernel(int n_seg, int S, double interval, double step, const double *__rest
             vs[j] = c1 + t * (T(2) * c2 + t * (T(3) * c3 + t * (T(4) * c4 + t * (T(5) * c5))));  // :218
             as[j] = T(2) * c2 + t * (T(6) * c3 + t * (T(12) * c4 + t * (T(20) * c5)));           // :220
         }
-        rne_core<T, DYN, TOOL, P>(qs, vs, as, mp_inertial, mp_tool, tau, prm);
+        if constexpr (kTable) rne_core_table<DYN, TOOL, P>(qs, vs, as, mp_inertial, mp_tool, tau, tab, prm);
+        else rne_core<T, DYN, TOOL, P>(qs, vs, as, mp_inertial, mp_tool, tau, prm);
         const bool ok = limits_ok<T, P>(tau, prm);
 #pragma unroll
         for (int j = 0; j < 7; ++j) {

@@ -14,11 +14,27 @@
 
 namespace tcmp {
 
+static __device__ const SinCos kModelSinCosTable[kSinCosTableSize] = {
+#include "sincos_table.inc"
+};
+
+// 2 CTAs / SM (194 registers: ptxas keeps the 55 parameters in registers).  Asking for 3 like K1 (168 registers) makes
+// it spill 184 B instead of re-reading the constant bank: 15.4 against 16.8 G states/s (profiles/r02/
+// extras_variants.log); the table-driven sincos is worth +5 % here (16.0 -> 16.8).
+#ifndef TCMP_MODEL_MIN_BLOCKS
+#define TCMP_MODEL_MIN_BLOCKS 2
+#endif
 template <typename T, bool DYN, bool TOOL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TCMP_MODEL_MIN_BLOCKS)
 rne_model_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, const T *__restrict__ qdd,
                  const T *__restrict__ payload_mass, T payload_scalar, T payload_threshold, T *__restrict__ tau_out,
                  uint8_t *__restrict__ feasible_out, const __grid_constant__ RtParams<T> P) {
+    constexpr bool kTable = sizeof(T) == 8 && DYN;    // table-driven sincos, as in K1
+    __shared__ SinCos tab[kTable ? kSinCosTableSize : 1];
+    if constexpr (kTable) {
+        for (int t = threadIdx.x; t < kSinCosTableSize; t += blockDim.x) tab[t] = kModelSinCosTable[t];
+        __syncthreads();
+    }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         T qs[7], vs[7], as[7], tau[7];
@@ -34,7 +50,8 @@ rne_model_kernel(int64_t n, const T *__restrict__ q, const T *__restrict__ qd, c
         // same payload rule as K1-K3: rigid body iff mass > threshold (rne / nov), tool-point force (dyn)
         const T mp_inertial = TOOL ? T(0) : (mass > payload_threshold ? mass : T(0));
         const T mp_tool = TOOL ? mass : T(0);
-        rne_core<T, DYN, TOOL, RtParams<T>>(qs, vs, as, mp_inertial, mp_tool, tau, P);
+        if constexpr (kTable) rne_core_table<DYN, TOOL, RtParams<T>>(qs, vs, as, mp_inertial, mp_tool, tau, tab, P);
+        else rne_core<T, DYN, TOOL, RtParams<T>>(qs, vs, as, mp_inertial, mp_tool, tau, P);
         if (tau_out) {
 #pragma unroll
             for (int j = 0; j < 7; ++j) __stcs(tau_out + j * n + i, tau[j]);

@@ -446,6 +446,9 @@ TCMP_FN void sincos6(const T (&q)[7], T (&s)[7], T (&c)[7]) {
 // sends the whole state down CUDA's sincos() as before.
 struct alignas(16) SinCos { double s, c; };
 constexpr int kSinCosTableSize = 1024;
+// GLOBAL = false: `tab` is the CTA's shared-memory copy; true: the table is read in place through the read-only
+// data cache (kernels whose shared memory is spoken for, or whose torque tests are too sparse to pay for staging).
+template <bool GLOBAL = false>
 TCMP_FN bool sincos6_table(const double (&q)[7], double (&s)[7], double (&c)[7], const SinCos *__restrict__ tab) {
     bool fast = true;
 #pragma unroll
@@ -454,7 +457,15 @@ TCMP_FN bool sincos6_table(const double (&q)[7], double (&s)[7], double (&c)[7],
 #pragma unroll
     for (int j = 1; j < 7; ++j) {
         const double kt = fma(q[j], 162.97466172610082 /* 512 / pi */, 6755399441055744.0);   // rint via 1.5 * 2^52
-        const SinCos e = tab[lo_word(kt) & (kSinCosTableSize - 1)];
+        SinCos e;
+#ifdef __CUDA_ARCH__
+        if constexpr (GLOBAL) {
+            const double2 v = __ldg(reinterpret_cast<const double2 *>(tab) + (lo_word(kt) & (kSinCosTableSize - 1)));
+            e.s = v.x;
+            e.c = v.y;
+        } else
+#endif
+            e = tab[lo_word(kt) & (kSinCosTableSize - 1)];
         const double kd = kt - 6755399441055744.0;
         // pi/512 = h1 + h2 + ...: fdlibm's 33-bit pieces of pi/2 scaled by 2^-8 (k < 2^20 keeps k h1, k h2 exact)
         double r = fma(-kd, 1.57079632673412561417e+00 / 256, q[j]);
@@ -548,16 +559,16 @@ TCMP_FN void rne_core(const T (&q)[7], const T (&qd)[7], const T (&qdd)[7], T mp
     rne_body<T, DYN, TOOL, P>(s, c, qd, qdd, mp_inertial, mp_tool, tau, p);
 }
 
-// K1's form: sin / cos from the shared-memory table when every angle allows it.
-template <bool DYN, bool TOOL>
+// K1's form: sin / cos from the table (shared-memory copy, or GLOBAL = in place) when every angle allows it.
+template <bool DYN, bool TOOL, typename P = ConstParams, bool GLOBAL = false>
 TCMP_FN void rne_core_table(const double (&q)[7], const double (&qd)[7], const double (&qdd)[7], double mp_inertial,
-                            double mp_tool, double (&tau)[7], const SinCos *__restrict__ tab) {
+                            double mp_tool, double (&tau)[7], const SinCos *__restrict__ tab, const P &p = P()) {
     double c[7], s[7];
-    if (!sincos6_table(q, s, c, tab)) {
+    if (!sincos6_table<GLOBAL>(q, s, c, tab)) {
 #pragma unroll
         for (int j = 1; j < 7; ++j) sincos_t<double>(q[j], &s[j], &c[j]);
     }
-    rne_body<double, DYN, TOOL, ConstParams>(s, c, qd, qdd, mp_inertial, mp_tool, tau);
+    rne_body<double, DYN, TOOL, P>(s, c, qd, qdd, mp_inertial, mp_tool, tau, p);
 }
 
 // |tau_i| < limit_i for i in 0..5 (panda_primitives.py:182-183; joint 7 is never tested).

@@ -13,6 +13,13 @@
 
 namespace tcmp {
 
+// (sin, cos)(i pi / 512) for the table-driven sincos of the static torque tests (panda_model.cuh sincos6_table<GLOBAL>):
+// read in place through the read-only cache -- this kernel's shared memory is spoken for, and its torque tests are
+// too few per CTA to pay for staging 16 KB.  Own copy per translation unit (no relocatable device code in the build).
+static __device__ const SinCos kSelSinCosTable[kSinCosTableSize] = {
+#include "sincos_table.inc"
+};
+
 struct JointLimits {
     double lo[7], hi[7];
 };
@@ -110,7 +117,7 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
                 if (check_torque) {
                     double tau[7];
                     const double z[7] = {0, 0, 0, 0, 0, 0, 0};
-                    rne_core<double, false, TOOL, P>(q, z, z, mp_inertial, mp_tool, tau, prm);
+                    rne_core_table<false, TOOL, P, true>(q, z, z, mp_inertial, mp_tool, tau, kSelSinCosTable, prm);   // table read in place (__ldg)
                     ok = limits_ok<double, P>(tau, prm);
                 }
                 if (ok) {

@@ -432,6 +432,8 @@ int tcmp_workspace_create(tcmp_workspace **out, int64_t chunk_states) {
     for (int s = 0; e == cudaSuccess && s < tcmp_workspace::kStages; ++s)
         e = cudaStreamCreateWithFlags(&ws->stream[s], cudaStreamNonBlocking);
     if (e != cudaSuccess) {
+        for (int s = 0; s < tcmp_workspace::kStages; ++s)      // streams created before the failure
+            if (ws->stream[s]) cudaStreamDestroy(ws->stream[s]);
         delete ws;
         return cuda_fail(e, "tcmp_workspace_create");
     }

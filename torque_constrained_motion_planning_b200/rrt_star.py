@@ -121,8 +121,17 @@ def _fused_prefix(sequence, collision, torque):
     from . import engine
     q1 = np.asarray(sequence.q1, dtype=float).reshape(7, 1)
     q2 = np.asarray(sequence.q2, dtype=float).reshape(7, 1)
-    _, pre = engine.extend_prefix(q1, q2, sequence.resolutions, scene["packed"], torque.mass(), mode=torque.mode,
-                                  model=getattr(torque, "model", None))
+    n_host = sequence.num_configs()
+    if n_host is None:
+        return None              # non-finite end point: let the per-configuration path deal with it
+    n_dev, pre = engine.extend_prefix(q1, q2, sequence.resolutions, scene["packed"], torque.mass(), mode=torque.mode,
+                                      model=getattr(torque, "model", None))
+    # The kernel counts the steps with a sequentially rounded sum, the host (like the reference) with
+    # np.linalg.norm, i.e. a BLAS dot with its own ordering; when the norm lands on an integer (axis-aligned moves
+    # at resolution 0.1) the two can differ by one step, and a prefix computed for another step count must not
+    # truncate this sequence: fall back to the unfused path for that edge.
+    if int(n_dev[0]) != n_host:
+        return None
     keep = int(pre[0])
     out = []
     for q in sequence:

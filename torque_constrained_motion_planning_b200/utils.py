@@ -111,9 +111,16 @@ class ExtendSequence:
         self.q1, self.q2, self.resolutions, self.norm = q1, q2, resolutions, norm
         self._body, self._joints = body, joints
 
+    def _norm(self):
+        return np.linalg.norm(np.divide(np.asarray(self.q2) - np.asarray(self.q1), self.resolutions), ord=self.norm)
+
+    def num_configs(self):
+        """Number of configurations iteration yields (steps + 1), or None when the norm is not finite."""
+        nrm = self._norm()
+        return int(nrm) + 1 if np.isfinite(nrm) and nrm < 1.0e6 else None
+
     def __iter__(self):
-        steps = int(np.linalg.norm(np.divide(np.asarray(self.q2) - np.asarray(self.q1), self.resolutions),
-                                   ord=self.norm))
+        steps = int(self._norm())
         return get_refine_fn(self._body, self._joints, num_steps=steps)(self.q1, self.q2)
 
 
