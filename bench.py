@@ -446,6 +446,9 @@ def main():
     ap.add_argument("--eager", action="store_true", help="time K Python launches instead of one captured CUDA graph")
     ap.add_argument("--settle-s", type=float, default=1.0,
                     help="seconds the step is held before the timed region (same sustained clock regime at every N)")
+    ap.add_argument("--multicast", action="store_true",
+                    help="p2p gather through NVSwitch multicast stores (tcmp_rne_batch_scatter_mc, torch symmetric memory) "
+                         "instead of unicast peer stores; measured within 1 %% of each other at N = 8")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the feasibility masks are all-gathered each step: p2p = peer stores fused into the "
                          "torque kernel (tcmp_rne_batch_scatter) + completion flags (tcmp_peer_signal / tcmp_peer_wait) on "
@@ -484,7 +487,8 @@ def main():
         gather = OverlappedGather((N_STATES,), torch.uint8, dev)
     elif world > 1:
         try:
-            peer = PeerMaskBuffer(N_STATES)   # gathered [2][world][N_STATES] mask buffer, written by every rank's kernel
+            # gathered [3][world][N_STATES] mask buffer, written by every rank's kernel
+            peer = PeerMaskBuffer(N_STATES, multicast=args.multicast)
             ok_flag = torch.ones(1, device=dev)
         except Exception as e:                # CUDA IPC unavailable in this container: every rank must agree
             print("rank %d: peer-store gather unavailable (%s)" % (rank, e), file=sys.stderr)
@@ -813,8 +817,9 @@ def main():
             },
             "modes": modes,
             "gather": "none (N = 1)" if world == 1 else
-                      ("p2p: peer stores fused into the torque kernel; tcmp_peer_signal + tcmp_peer_wait per step on a side "
-                       "stream, joined inside the timed region"
+                      (("p2p/NVLS: NVSwitch multicast stores (multimem.st) fused into the torque kernel"
+                        if peer.mc_ptr else "p2p: peer stores fused into the torque kernel") +
+                       "; tcmp_peer_signal + tcmp_peer_wait per step on a side stream, joined inside the timed region"
                        if peer is not None else args.gather),
             "gather_check": gather_check,
             "extras": extras,

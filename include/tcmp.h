@@ -115,6 +115,19 @@ int tcmp_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const 
                            void *tau_out, int n_dest, void *const *dest_masks, int64_t dest_offset,
                            void *stream);
 /*
+ * NVLS form of tcmp_rne_batch_scatter: the gathered buffers are ALSO mapped at one NVSwitch multicast address
+ * (mc_masks: cuMulticast* / torch symmetric memory's multicast_ptr; same layout, same dest_offset).  Full warps store
+ * their 32 verdicts with two 16-byte multimem.st -- the switch replicates them into every rank's buffer, so a step
+ * issues 1/n_dest of the store requests and outgoing NVLink bytes of the unicast form.  The batch's last partial warp
+ * (multimem.st has no byte form) goes through dest_masks as in tcmp_rne_batch_scatter, which therefore must be the
+ * unicast mappings of the same buffers.  `base` mode and a dest_offset that is not a multiple of 16 take the unicast
+ * path entirely.
+ */
+int tcmp_rne_batch_scatter_mc(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
+                              const void *payload_mass, double payload_scalar, double payload_threshold,
+                              void *tau_out, int n_dest, void *const *dest_masks, void *mc_masks, int64_t dest_offset,
+                              void *stream);
+/*
  * Completion flags of the fused gathers (no host barrier, no collective call, CUDA-graph capturable).  Every rank owns
  * a sync block (TCMP_PEER_SYNC_BYTES of tcmp_peer_alloc memory, which arrives zeroed; dest_sync[r] = rank r's block as
  * mapped on this rank, dest_sync[rank] = this rank's own).

@@ -5,6 +5,7 @@
   A  scatter kernel only (peer stores, no completion flags)               -- producer-only, as round 1 timed it
   F  A + tcmp_peer_signal + tcmp_peer_wait in the same stream after every step
   G  A + signal / wait on a side stream under the next step's kernel (PeerMaskBuffer overlap_gather=True)
+  M  G with the peer stores replaced by NVSwitch multicast stores (tcmp_rne_batch_scatter_mc, multimem.st)
   H  plain kernel, then on the side stream tcmp_peer_push (copy the local mask block to every rank) + signal / wait
 Each: 200 steps captured in one CUDA graph, replayed 20x after a barrier, max over ranks.
 (The in-kernel completion-flag tail measured in profiles/r02/scatter_signal_variants.log was removed.)
@@ -30,7 +31,8 @@ dev = torch.device("cuda", local)
 sets = [tuple(torch.as_tensor(a, device=dev) for a in sample_states(N_STATES, 2 + 1000 * rank + s)) for s in range(4)]
 out_tau = torch.empty((7, N_STATES), dtype=torch.float64, device=dev)
 out_mask = torch.empty((N_STATES,), dtype=torch.uint8, device=dev)
-peer = PeerMaskBuffer(N_STATES)
+peer = PeerMaskBuffer(N_STATES, multicast=False)      # unicast peer stores (CUDA IPC mappings)
+peer_mc = PeerMaskBuffer(N_STATES, multicast=True)    # NVLS: symmetric memory + multicast address, when the box has it
 
 
 def var_a(i):
@@ -56,6 +58,10 @@ def var_h(i):
     peer.push(ok)
 
 
+def var_m(i):
+    peer_mc.torque_test(*sets[i % 4], mode="rne", out_tau=out_tau, overlap_gather=True)
+
+
 def var_e(i):
     engine.torque_test_batch(*sets[i % 4], mode="rne", out_tau=out_tau, out_mask=out_mask)
 
@@ -69,12 +75,15 @@ def capture(fn, k=200):
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     peer.reset()
+    peer_mc.reset()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g, stream=side):
         for i in range(k):
             fn(i)
         peer.join()
+        peer_mc.join()
     peer.reset()
+    peer_mc.reset()
     return g
 
 
@@ -95,7 +104,9 @@ def timeit(g, reps=20, k=200):
 
 res = {}
 for name, fn in (("E_plain", var_e), ("A_scatter", var_a), ("F_signal_wait_in_stream", var_f),
-                 ("G_signal_wait_side_stream", var_g), ("H_unfused_push_side_stream", var_h), ("E_plain_again", var_e)):
+                 ("G_signal_wait_side_stream", var_g), ("H_unfused_push_side_stream", var_h),
+                 ("M_multicast_side_stream" if peer_mc.mc_ptr else "M_multicast_unavailable_unicast", var_m),
+                 ("E_plain_again", var_e)):
     res[name] = timeit(capture(fn))
 if rank == 0:
     print(json.dumps({"world": world, "lib": os.path.basename(os.environ.get("TCMP_LIB", "libtcmp.so")), "us_per_step": res}))

@@ -40,6 +40,8 @@ SIGNATURES = {
     "tcmp_extend_prefix_model": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _f64, _f64, _f64, _vp, _vp, _vp]),
     "tcmp_rne_batch_scatter": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _i32,
                                       ctypes.POINTER(_vp), _i64, _vp]),
+    "tcmp_rne_batch_scatter_mc": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _i32,
+                                         ctypes.POINTER(_vp), _vp, _i64, _vp]),
     "tcmp_peer_push": (_i32, [_vp, _i64, _i32, ctypes.POINTER(_vp), _i64, _vp]),
     "tcmp_peer_signal": (_i32, [_i32, _i32, ctypes.POINTER(_vp), _vp]),
     "tcmp_peer_wait": (_i32, [_vp, _i32, _vp]),

@@ -45,6 +45,7 @@ struct MaskDests {
     uint8_t *p[TCMP_MAX_PEERS];
     int n;
     int64_t offset;
+    uint8_t *mc;       // NVSwitch multicast address of the same gathered buffer (or nullptr): one store reaches every rank
 };
 
 // sync blocks of all ranks as one kernel argument (tcmp_peer_signal)
@@ -53,12 +54,39 @@ struct SyncDests {
     int n_sync, rank;
 };
 
-// Scatter epilogue: the 32 lanes of a warp store 32 consecutive mask bytes into every rank's gathered buffer -- one
-// 32-byte sector request per peer per warp round.  (Packing the verdicts with a ballot into 16-byte vector stores, one
-// store instruction for all peers, was measured at N = 8: 54.1 us per step against 52.7 us for these byte stores -- the
-// hardware already coalesces the byte lanes, the vector form only doubles the request count.)
+// Scatter epilogue: the 32 lanes of a warp store 32 consecutive mask bytes into every rank's gathered buffer.
+//  * unicast (peer pointers): one byte store per lane per peer -- one 32-byte sector request per peer per warp round.
+//    (Packing the verdicts with a ballot into 16-byte vector stores per peer was measured at N = 8: 54.1 us per step
+//    against 52.7 us for the byte stores -- the hardware already coalesces the byte lanes.)
+//  * multicast (dests.mc, NVLS): the buffer is also mapped at an NVSwitch multicast address; the warp ballots its 32
+//    verdicts, lanes 0 and 1 each issue ONE 16-byte multimem.st and the switch replicates it to every rank -- 1/8 of
+//    the store requests and of the outgoing NVLink bytes at N = 8.  multimem.st has no byte form, so a partial warp
+//    (the batch's tail) or a misaligned destination takes the unicast path.  Measured at N = 8: 53.7 us per step
+//    against 54.1 us unicast (plain kernel 48.2-50.7): what the gather costs is receiving 8 MB of small writes per
+//    rank per step and draining the last CTAs' remote stores, not issuing them (profiles/r02/scatter_signal_variants.log),
+//    so the unicast form stays the default and this one is opt-in (PeerMaskBuffer(multicast=True)).
 template <typename I>
-__device__ __forceinline__ void scatter_mask(const MaskDests &dests, I at, bool ok) {
+__device__ __forceinline__ void scatter_mask(const MaskDests &dests, I at, I n, bool ok) {
+    if (dests.mc) {
+        const int lane = threadIdx.x & 31;
+        const I base = at - (I)lane;
+        if (base + 32 <= n) {                       // warp-uniform: all 32 lanes are in this round
+            const unsigned b = __ballot_sync(0xffffffffu, ok);
+            if (lane < 2) {
+                const unsigned h16 = (b >> (lane * 16)) & 0xffffu;
+                // 4 verdict bits -> 4 bytes 0 / 1
+                auto spread = [](unsigned x) { return (x & 1u) | ((x & 2u) << 7) | ((x & 4u) << 14) | ((x & 8u) << 21); };
+                const unsigned w0 = spread(h16 & 0xfu), w1 = spread((h16 >> 4) & 0xfu),
+                               w2 = spread((h16 >> 8) & 0xfu), w3 = spread((h16 >> 12) & 0xfu);
+                uint8_t *dst = dests.mc + dests.offset + base + lane * 16;
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst),
+                             "f"(__uint_as_float(w0)), "f"(__uint_as_float(w1)), "f"(__uint_as_float(w2)),
+                             "f"(__uint_as_float(w3))
+                             : "memory");
+            }
+            return;
+        }
+    }
     const uint8_t m = (uint8_t)ok;
 #pragma unroll
     for (int d = 0; d < TCMP_MAX_PEERS; ++d)   // unrolled: constant indices keep `dests` in param space
@@ -128,7 +156,7 @@ rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T
             for (int j = 0; j < 7; ++j) __stcs(tau_out + j * n + at, tau[j]);
         }
         if constexpr (SCATTER) {
-            scatter_mask<I>(dests, at, within_limits<T>(tau));
+            scatter_mask<I>(dests, at, n, within_limits<T>(tau));
         } else if constexpr (WRITE_MASK) {
             __stcs(feasible_out + at, (uint8_t)within_limits<T>(tau));
         }
@@ -176,7 +204,7 @@ rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T
             for (int j = 0; j < 7; ++j) __stcs(tau_out + j * n + i, tau[j]);
         }
         if constexpr (SCATTER) {
-            scatter_mask<I>(dests, i, within_limits<T>(tau));
+            scatter_mask<I>(dests, i, n, within_limits<T>(tau));
         } else if constexpr (WRITE_MASK) {
             __stcs(feasible_out + i, (uint8_t)within_limits<T>(tau));
         }
@@ -375,11 +403,13 @@ cudaError_t launch_peer_wait(void *own_sync, int world, cudaStream_t st) {
 
 cudaError_t launch_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
                                      const void *pm, double ps, double pt, void *tau, int n_dest,
-                                     void *const *dest_masks, int64_t dest_offset, cudaStream_t st) {
+                                     void *const *dest_masks, int64_t dest_offset, cudaStream_t st, void *mc_masks) {
     MaskDests d = {};
     d.n = n_dest;
     d.offset = dest_offset;
     for (int i = 0; i < TCMP_MAX_PEERS; ++i) d.p[i] = i < n_dest ? (uint8_t *)dest_masks[i] : nullptr;
+    // the 16-byte multicast stores need a 16-byte aligned destination (the warp's base index is a multiple of 32)
+    d.mc = (mc_masks && ((uintptr_t)mc_masks + (uintptr_t)dest_offset) % 16 == 0) ? (uint8_t *)mc_masks : nullptr;
     if (dtype != TCMP_F64) return cudaErrorNotSupported;
     const bool dynamic = (mode != TCMP_MODE_NOV) && qd && qdd;
     const bool tool = (mode == TCMP_MODE_DYN);

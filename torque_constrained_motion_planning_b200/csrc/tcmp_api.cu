@@ -221,6 +221,25 @@ int tcmp_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const 
     return TCMP_OK;
 }
 
+int tcmp_rne_batch_scatter_mc(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
+                              const void *payload_mass, double payload_scalar, double payload_threshold, void *tau_out,
+                              int n_dest, void *const *dest_masks, void *mc_masks, int64_t dest_offset, void *stream) {
+    if (!mc_masks) return fail(TCMP_ERR_INVALID_ARG, "mc_masks is NULL (use tcmp_rne_batch_scatter)");
+    if (int rc = check_common(mode, dtype, n)) return rc;
+    if (dtype != TCMP_F64) return fail(TCMP_ERR_UNSUPPORTED, "scatter form is fp64 only");
+    if (n_dest < 1 || n_dest > TCMP_MAX_PEERS || !dest_masks || dest_offset < 0)
+        return fail(TCMP_ERR_INVALID_ARG, "bad destination list");
+    for (int i = 0; i < n_dest; ++i)
+        if (!dest_masks[i]) return fail(TCMP_ERR_INVALID_ARG, "dest_masks[%d] is NULL", i);
+    if (n == 0) return TCMP_OK;
+    if (!q && mode != TCMP_MODE_BASE) return fail(TCMP_ERR_INVALID_ARG, "q is NULL");
+    if ((qd == nullptr) != (qdd == nullptr))
+        return fail(TCMP_ERR_INVALID_ARG, "qd and qdd must both be given or both be NULL");
+    TCMP_CUDA(launch_rne_batch_scatter(mode, dtype, n, q, qd, qdd, payload_mass, payload_scalar, payload_threshold,
+                                       tau_out, n_dest, dest_masks, dest_offset, (cudaStream_t)stream, mc_masks));
+    return TCMP_OK;
+}
+
 int tcmp_peer_push(const void *src, int64_t bytes, int n_dest, void *const *dests, int64_t dest_offset, void *stream) {
     if (bytes < 0 || n_dest < 1 || n_dest > TCMP_MAX_PEERS || !dests || dest_offset < 0)
         return fail(TCMP_ERR_INVALID_ARG, "bad push arguments");

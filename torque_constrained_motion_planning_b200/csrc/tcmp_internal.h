@@ -57,7 +57,7 @@ static_assert(sizeof(PeerSync) == TCMP_PEER_SYNC_BYTES, "tcmp.h: TCMP_PEER_SYNC_
 cudaError_t launch_rne_batch_scatter(int mode, int dtype, int64_t n, const void *q, const void *qd, const void *qdd,
                                      const void *payload_mass, double payload_scalar, double payload_threshold,
                                      void *tau_out, int n_dest, void *const *dest_masks, int64_t dest_offset,
-                                     cudaStream_t st);
+                                     cudaStream_t st, void *mc_masks = nullptr);
 cudaError_t launch_peer_signal(int rank, int n_dest, void *const *dest_sync, cudaStream_t st);
 cudaError_t launch_peer_push(const void *src, int64_t bytes, int n_dest, void *const *dests, int64_t dest_offset,
                              cudaStream_t st);
