@@ -429,103 +429,142 @@ TCMP_HD TCMP_OUTLINE inline int solve_elbow_singular(const Pose &P, Root *j3p, c
     return 0;   // "branch miss [j4]" (:2849): K ~ 0 away from both special angles cannot happen for real j3
 }
 
-// One solve (IKSolver::ComputeIk, :412).  WITH_ELBOW = false is the kernels' hot path: it carries everything but the
-// elbow-singularity branches (1 solve in ~10^5 of a random sweep, every solve of a pose with joint 4 at 2.63084 / 0) and
-// bails out with kStatusRedo when it meets one; inlining those branches costs the hot path 36 registers (128 -> 164).
-template <bool WITH_ELBOW>
-TCMP_HD inline void solve_one_t(const Pose &P, Emit &out) {
-    const double cn = xmul(P.c6, P.npx);  // x78
-    const double sn = xmul(P.npy, P.s6);  // x79
+// ---- one solve (IKSolver::ComputeIk, :412), split so that a kernel can re-balance its lanes between the stages -----
+//
+//   plan_roots   everything that precedes the per-root work: j3 from |p|^2 (two roots of one asin, duplicate test,
+//                :461-501), the root-independent guards and quantities of the j5 formula (:503-508, :2351-2360), and for
+//                each j3 root whether it survives to the j5 roots (asin argument in range, :2361-2363).
+//   solve_root   one j3 root: j5 (two roots), j4, the residual shoulder problem -- up to 4 solutions.
+//
+// A solve is plan_roots + solve_root for every live root, in root order (solve_one_t).  ~45 % of a sweep's solves have no
+// live root, ~29 % one, ~27 % two: a warp that runs 32 solves through one loop idles a third of its lanes, so the batch
+// kernel sorts planned solves into a one-root and a two-root queue and runs solve_root on homogeneous batches.
+struct RootPlan {
+    Root j3[2];
+    bool live[2];      // the root reaches the j5 roots
+    double cn, sn;     // x78 = cj6 npx, x79 = npy sj6
+    double x975, at5;  // 0.088 - cn + sn;  atan2(npz, x975)
+    double hinv;       // 1 / |(x975, npz)|
+};
+
+// Returns the number of live roots (0: the solve is finished, out.status says why when it is not a plain "no solution").
+TCMP_HD inline int plan_roots(const Pose &P, RootPlan &pl, Emit &out) {
+    pl.live[0] = pl.live[1] = false;
+    pl.cn = xmul(P.c6, P.npx);
+    pl.sn = xmul(P.npy, P.s6);
     // j3 from |p|^2 (:461-485)
     const double arg3 = j3_asin_argument(P);
     if (!(arg3 == arg3)) {   // NaN anywhere in the pose / free value ends up here
         out.status |= kStatusInvalid;
-        return;
+        return 0;
     }
-    if (!in_unit(arg3)) return;
+    if (!in_unit(arg3)) return 0;
     const double a3 = clamp_asin(arg3);
-    Root j3r[2] = {make_root(1.10379390314189 + a3), make_root(4.24538655673168 - a3)};
-    bool j3ok[2] = {true, !same_root(j3r[0], j3r[1])};
-    if (same_root_borderline(j3r[0], j3r[1])) out.status |= kStatusIllConditioned;
+    pl.j3[0] = make_root(1.10379390314189 + a3);
+    pl.j3[1] = make_root(4.24538655673168 - a3);
+    const bool second = !same_root(pl.j3[0], pl.j3[1]);
+    if (same_root_borderline(pl.j3[0], pl.j3[1])) out.status |= kStatusIllConditioned;
+    // branch guards for the j5 formula (:503-508); none of this depends on the j3 root
+    const double cn = pl.cn, sn = pl.sn;
+    const double g0 = 1.0 + 129.132231404959 * (cn * cn) + 22.7272727272727 * sn + 129.132231404959 * (sn * sn) +
+                      (-258.264462809917) * cn * sn + 129.132231404959 * (P.npz * P.npz) + (-22.7272727272727) * cn;
+    pl.x975 = xadd(xsub(0.088, cn), sn);
+    const double g1 = fabs(pl.x975) + fabs(P.npz);
+    if (fabs(g0) < kBranchThresh || fabs(g1) < kBranchThresh) {
+        // Shoulder centre within 8.8e-5 m of the joint-6 axis (g0 = 129.13 h^2, h the distance).  The generated
+        // sub-tree (:509-2346) solves j4 from asin(U / K) first and j5 from a quotient by h^2, but each of its j5
+        // formulas is guarded by the same g0 (times 1, sin j4 or cos j4) and ends in "no branches", and its doubly
+        // singular part (:516-1575, j3 ~ 2.63084 as well) needs |2.6e9 U| <= 1 where |U| = 0.068 on this axis.
+        // The geometry agrees: 0.384 + 0.316 cos j3 - 0.0825 sin j3 >= 0.057 > h, no configuration puts the
+        // shoulder there.  So: 0 solutions, resolved (the compiled reference returns 0 on every such pose of
+        // tests/ik_families.py:wrist_axis_family).
+        out.status |= kStatusDegenerate;
+        return 0;
+    }
+    // j5: atan2 + asin (:2347-2364)
+    if (!atan2_checked(P.npz, pl.x975, &pl.at5)) return 0;
+    const double h2 = xadd(xmul(pl.x975, pl.x975), xmul(P.npz, P.npz));
+    if (h2 < -0.00001) return 0;
+    const double h = fabs(h2 <= 0.0 ? 0.0 : sqrt(h2));   // IKabs(IKsqrt(.)) (:183)
+    if (h == 0.0) return 0;                              // IKPowWithIntegerCheck(.,-1) (:269)
+    pl.hinv = 1.0 / h;
+    int n_live = 0;
+    for (int r = 0; r < 2; ++r) {
+        if (r == 1 && !second) break;
+        const double arg5 = xmul(pl.hinv, xadd(xadd(0.384, xmul(-0.0825, pl.j3[r].s)), xmul(0.316, pl.j3[r].c)));
+        pl.live[r] = in_unit(arg5);
+        n_live += pl.live[r];
+    }
+    return n_live;
+}
+
+// One live j3 root (:2365-3097 + rotationfunction0).  WITH_ELBOW = false is the kernels' hot path: it carries everything
+// but the elbow-singularity branches (1 solve in ~10^5 of a random sweep, every solve of a pose with joint 4 at 2.63084
+// or 0) and bails out with kStatusRedo when it meets one; inlining those branches costs the hot path 36 registers.
+template <bool WITH_ELBOW>
+TCMP_HD inline void solve_root(const Pose &P, const RootPlan &pl, const Root &j3, Emit &out) {
+    const double arg5 = xmul(pl.hinv, xadd(xadd(0.384, xmul(-0.0825, j3.s)), xmul(0.316, j3.c)));
+    const double a5 = clamp_asin(arg5);
+    const double at5 = pl.at5;
+    Root j5r[2] = {make_root(-a5 - at5), make_root(3.14159265358979 + a5 - at5)};
+    bool j5ok[2] = {true, !same_root(j5r[0], j5r[1])};
+    if (same_root_borderline(j5r[0], j5r[1])) out.status |= kStatusIllConditioned;
 
 TCMP_ROOT_LOOP
-    for (int i3 = 0; i3 < 2; ++i3) {
-        if (!j3ok[i3]) continue;
-        const Root &j3 = j3r[i3];
-        // branch guards for the j5 formula (:503-508)
-        const double g0 = 1.0 + 129.132231404959 * (cn * cn) + 22.7272727272727 * sn + 129.132231404959 * (sn * sn) +
-                          (-258.264462809917) * cn * sn + 129.132231404959 * (P.npz * P.npz) +
-                          (-22.7272727272727) * cn;
-        const double x975 = xadd(xsub(0.088, cn), sn);
-        const double g1 = fabs(x975) + fabs(P.npz);
-        if (fabs(g0) < kBranchThresh || fabs(g1) < kBranchThresh) {
-            // Shoulder centre within 8.8e-5 m of the joint-6 axis (g0 = 129.13 h^2, h the distance).  The generated
-            // sub-tree (:509-2346) solves j4 from asin(U / K) first and j5 from a quotient by h^2, but each of its j5
-            // formulas is guarded by the same g0 (times 1, sin j4 or cos j4) and ends in "no branches", and its doubly
-            // singular part (:516-1575, j3 ~ 2.63084 as well) needs |2.6e9 U| <= 1 where |U| = 0.068 on this axis.
-            // The geometry agrees: 0.384 + 0.316 cos j3 - 0.0825 sin j3 >= 0.057 > h, no configuration puts the
-            // shoulder there.  So: 0 solutions, resolved (the compiled reference returns 0 on every such pose of
-            // scripts/ik_structured_families.py:wrist_axis_family).
+    for (int i5 = 0; i5 < 2; ++i5) {
+        if (!j5ok[i5]) continue;
+        const Root &j5 = j5r[i5];
+        // j4: one root (:2404-2408 guards, :3037-3045 formula)
+        const double K = xadd(xadd(-0.0825, xmul(0.0825, j3.c)), xmul(0.316, j3.s));
+        const double U = xadd(xmul(P.c6, P.npy), xmul(P.npx, P.s6));
+        // (-0.088 cj5) + ((-cj5 npy) sj6) + (npz sj5) + ((cj5 cj6) npx)   (:2406, :3037)
+        const double W = xadd(xadd(xadd(xmul(-0.088, j5.c), xmul(xmul(-j5.c, P.npy), P.s6)), xmul(P.npz, j5.s)),
+                              xmul(xmul(j5.c, P.c6), P.npx));
+        const double q0 = xadd(xadd(-1.0, j3.c), xmul(3.83030303030303, j3.s));
+        const double sK = sign_of(K);
+        Root j3u = j3, j4c[2];
+        int n4;
+        if (near_threshold(fabs(q0), kBranchThresh) || near_threshold(fabs(U) + fabs(W), kBranchThresh))
+            out.status |= kStatusIllConditioned;
+        if (fabs(q0) < kBranchThresh || fabs(U) + fabs(W) < kBranchThresh || fabs(sK) < kBranchThresh) {
+            // Elbow singularity: K = 0, the shoulder centre lies on the forearm (joint-5) axis, so the position
+            // equations say nothing about j4 (U^2 + W^2 = K^2).
             out.status |= kStatusDegenerate;
-            continue;
-        }
-        // j5: two roots (:2347-2386)
-        double at5;
-        if (!atan2_checked(P.npz, x975, &at5)) continue;
-        const double h2 = xadd(xmul(x975, x975), xmul(P.npz, P.npz));
-        if (h2 < -0.00001) continue;
-        const double h = fabs(h2 <= 0.0 ? 0.0 : sqrt(h2));   // IKabs(IKsqrt(.)) (:183)
-        if (h == 0.0) continue;                              // IKPowWithIntegerCheck(.,-1) (:269)
-        const double arg5 = xmul(1.0 / h, xadd(xadd(0.384, xmul(-0.0825, j3.s)), xmul(0.316, j3.c)));
-        if (!in_unit(arg5)) continue;
-        const double a5 = clamp_asin(arg5);
-        Root j5r[2] = {make_root(-a5 - at5), make_root(3.14159265358979 + a5 - at5)};
-        bool j5ok[2] = {true, !same_root(j5r[0], j5r[1])};
-        if (same_root_borderline(j5r[0], j5r[1])) out.status |= kStatusIllConditioned;
-
-TCMP_ROOT_LOOP
-        for (int i5 = 0; i5 < 2; ++i5) {
-            if (!j5ok[i5]) continue;
-            const Root &j5 = j5r[i5];
-            // j4: one root (:2404-2408 guards, :3037-3045 formula)
-            const double K = xadd(xadd(-0.0825, xmul(0.0825, j3.c)), xmul(0.316, j3.s));
-            const double U = xadd(xmul(P.c6, P.npy), xmul(P.npx, P.s6));
-            // (-0.088 cj5) + ((-cj5 npy) sj6) + (npz sj5) + ((cj5 cj6) npx)   (:2406, :3037)
-            const double W = xadd(xadd(xadd(xmul(-0.088, j5.c), xmul(xmul(-j5.c, P.npy), P.s6)), xmul(P.npz, j5.s)),
-                                  xmul(xmul(j5.c, P.c6), P.npx));
-            const double q0 = xadd(xadd(-1.0, j3.c), xmul(3.83030303030303, j3.s));
-            const double sK = sign_of(K);
-            Root j3u = j3, j4c[2];
-            int n4;
-            if (near_threshold(fabs(q0), kBranchThresh) || near_threshold(fabs(U) + fabs(W), kBranchThresh))
-                out.status |= kStatusIllConditioned;
-            if (fabs(q0) < kBranchThresh || fabs(U) + fabs(W) < kBranchThresh || fabs(sK) < kBranchThresh) {
-                // Elbow singularity: K = 0, the shoulder centre lies on the forearm (joint-5) axis, so the position
-                // equations say nothing about j4 (U^2 + W^2 = K^2).
-                out.status |= kStatusDegenerate;
-                if (!WITH_ELBOW) {
-                    out.status |= kStatusRedo;
-                    return;
-                }
-                n4 = solve_elbow_singular(P, &j3u, j5, q0, U, W, j4c, out);
-            } else {
-                double at4;
-                if (!atan2_checked(U, W, &at4)) continue;
-                const Root j4 = make_root(-kHalfPiLit + at4 + kHalfPiLit * (1.0 / sK));
-                // 4 residuals (:3087-3090)
-                const double e0 = j4.s * K - U, e1 = j4.c * K - W, e2 = j4.c * U - j4.s * W,
-                             e3 = K - j4.c * W - j4.s * U;
-                if (fabs(e0) > kEvalThresh || fabs(e1) > kEvalThresh || fabs(e2) > kEvalThresh || fabs(e3) > kEvalThresh)
-                    continue;
-                j4c[0] = j4;
-                n4 = 1;
+            if (!WITH_ELBOW) {
+                out.status |= kStatusRedo;
+                return;
             }
-            // one call site: solve_shoulder is by far the largest inlined body of the kernel
+            n4 = solve_elbow_singular(P, &j3u, j5, q0, U, W, j4c, out);
+        } else {
+            double at4;
+            if (!atan2_checked(U, W, &at4)) continue;
+            const Root j4 = make_root(-kHalfPiLit + at4 + kHalfPiLit * (1.0 / sK));
+            // 4 residuals (:3087-3090)
+            const double e0 = j4.s * K - U, e1 = j4.c * K - W, e2 = j4.c * U - j4.s * W,
+                         e3 = K - j4.c * W - j4.s * U;
+            if (fabs(e0) > kEvalThresh || fabs(e1) > kEvalThresh || fabs(e2) > kEvalThresh || fabs(e3) > kEvalThresh)
+                continue;
+            j4c[0] = j4;
+            n4 = 1;
+        }
+        // one call site: solve_shoulder is by far the largest inlined body of the kernel
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
-            for (int i4 = 0; i4 < n4; ++i4) solve_shoulder(P, j3u, j4c[i4], j5, out);
-        }
+        for (int i4 = 0; i4 < n4; ++i4) solve_shoulder(P, j3u, j4c[i4], j5, out);
+    }
+}
+
+// The whole solve on one lane: plan, then the live roots in root order.
+template <bool WITH_ELBOW>
+TCMP_HD inline void solve_one_t(const Pose &P, Emit &out) {
+    RootPlan pl;
+    if (plan_roots(P, pl, out) == 0) return;
+TCMP_ROOT_LOOP
+    for (int i3 = 0; i3 < 2; ++i3) {
+        if (!pl.live[i3]) continue;
+        solve_root<WITH_ELBOW>(P, pl, pl.j3[i3], out);
+        if (!WITH_ELBOW && (out.status & kStatusRedo)) return;
     }
 }
 
