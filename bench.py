@@ -158,7 +158,8 @@ def cpu_baseline_run(n_sample, reps, nthreads=0):
     if n_sample not in _CPU_INPUTS:
         _CPU_INPUTS[n_sample] = sample_states(n_sample, seed=2)
     q, qd, qdd, mass = _CPU_INPUTS[n_sample]
-    oracle.torque_test_batch("rne", q[:, :20000], qd[:, :20000], qdd[:, :20000], mass[:20000], nthreads=nthreads)
+    for _ in range(2):      # thread pool, page tables and clocks warm, like the reference arm's warm-up steps
+        oracle.torque_test_batch("rne", q, qd, qdd, mass, nthreads=nthreads)
     t0 = time.perf_counter()
     for _ in range(reps):
         oracle.torque_test_batch("rne", q, qd, qdd, mass, nthreads=nthreads)
@@ -834,10 +835,10 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:
-            v, cores, dt = cpu_baseline_run(N_STATES, 3)
+            v, cores, dt = cpu_baseline_run(N_STATES, 10)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": "3 passes over the same 1M-state workload (%.1f s wall), C oracle port of "
-                                             "rne.py with OpenMP, inputs pre-generated" % dt,
+                                   "sample": "10 passes over the same 1M-state workload after 2 warm passes (%.1f s "
+                                             "wall), C oracle port of rne.py with OpenMP, inputs pre-generated" % dt,
                                    "python_port_states_per_s_per_core": python_port_rate(),
                                    "python_port_note": "oracle/rne_numpy_port.py: NumPy restatement at rne.py's own "
                                                        "per-call granularity (np.block / np.linalg.inv per link), "
