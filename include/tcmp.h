@@ -216,10 +216,12 @@ int tcmp_traj_feasibility(int mode, int dtype, int n_seg, int samples_per_segmen
  *       tie on a 1e-6 guard; none is reached by the structured singular-pose sweeps of tests/ (profiles/r02/
  *       ik_reference_coverage.md lists the reference's reached lines).
  *     bit 3 (8) = ill-conditioned count: a duplicate-root test (|d cos|, |d sin| < 1e-6, :495) or a singular-branch
- *       guard came within 1 % of its threshold.  Two roots 1e-6 apart come from an asin / acos argument 1.2e-13 from
+ *       guard came within 1 % of its threshold, or joint 4 lies within 6e-5 rad of the elbow singularity (|K| < 2e-5,
+ *       where j5's rounding residue reaches j4 amplified by C^2 / K^2).  Two roots 1e-6 apart come from an asin / acos argument 1.2e-13 from
  *       +-1, where one ulp of the argument moves them by 3e-10: the reference's own count then depends on its libm and
  *       compiler flags.  The host build of the solver (glibc, no contraction) returns the reference's solutions bit
- *       for bit; on the GPU (CUDA libm) 8 of 5.2 M structured singular solves differed, all with this bit set.
+ *       for bit; on the GPU (CUDA libm) 47 of 36 M structured singular solves differed, all with this bit set, and 0 of
+ *       100 M random-pose solves.
  *     bit 2 (4) = non-finite input (the reference throws from IKFAST_ASSERT; here the solve returns 0 solutions).
  */
 int tcmp_ik_batch(int64_t n, const double *rot9, const double *trans3, const double *free_vals,

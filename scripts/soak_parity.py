@@ -36,6 +36,22 @@ for r in range(rounds):
     _, cr = oracle.ref_ik_batch(rot.cpu().numpy(), trans.cpu().numpy(), free, want_sols=False, nthreads=NT)
     out["ik_solves"] += n * nf; out["ik_count_mismatches"] += int((c.cpu().numpy() != cr).sum())
     out["ik_status_nonzero"] += int((st != 0).sum().item())
+    stn = st.cpu().numpy()
+    out["ik_unflagged_mismatches"] = out.get("ik_unflagged_mismatches", 0) + int(((c.cpu().numpy() != cr) & ((stn & 10) == 0)).sum())
+# IK counts on the structured singular-pose families (tests/ik_families.py), a different seed than the test-suite's
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from ik_families import structured_families
+out["ik_structured_solves"] = 0; out["ik_structured_mismatches"] = 0; out["ik_structured_unflagged_mismatches"] = 0
+out["ik_structured_illconditioned"] = 0; out["ik_structured_unresolved"] = 0
+for name, (q, free) in structured_families(n_per=int(os.environ.get("IK_FAMILY_N", 60_000)), seed=2024).items():
+    trans, rot = oracle.ref_fk_batch(q)
+    _, cr = oracle.ref_ik_batch(rot, trans, free, want_sols=False, nthreads=NT)
+    _, c, st = engine.ik_batch(dev(rot), dev(trans), dev(free), want_sols=False)
+    c, st = c.cpu().numpy(), st.cpu().numpy()
+    bad = c != cr
+    out["ik_structured_solves"] += len(c); out["ik_structured_mismatches"] += int(bad.sum())
+    out["ik_structured_unflagged_mismatches"] += int((bad & ((st & 8) == 0)).sum())
+    out["ik_structured_illconditioned"] += int(((st & 8) != 0).sum()); out["ik_structured_unresolved"] += int(((st & 2) != 0).sum())
 # edges
 E = 1_000_000
 qa = rng.uniform(Q_LO[:, None], Q_HI[:, None], size=(7, E))

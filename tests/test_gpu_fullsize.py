@@ -147,7 +147,7 @@ def test_structured_singular_pose_families_five_million_solves(eng):
     assert total >= 5_000_000 and flagged > 100_000
     print("structured IK families: %d solves, %d ill-conditioned (bit 3), %d count mismatches (all ill-conditioned)"
           % (total, n_ill, n_mism))
-    assert n_mism <= 1e-5 * total and n_ill <= 2e-3 * total
+    assert n_mism <= 1e-5 * total and n_ill <= 0.2 * total      # every elbow-singular solve is flagged by construction
     rot, trans, free = wrist_axis_family(200_000)
     _, cr = oracle.ref_ik_batch(rot, trans, free, want_sols=False, nthreads=NT)
     _, counts, status = eng.ik_batch(dev(rot), dev(trans), dev(free), want_sols=False)

@@ -524,7 +524,11 @@ TCMP_ROOT_LOOP
         const double sK = sign_of(K);
         Root j3u = j3, j4c[2];
         int n4;
-        if (near_threshold(fabs(q0), kBranchThresh) || near_threshold(fabs(U) + fabs(W), kBranchThresh))
+        // Next to the elbow singularity j4 = atan2(U, W) with |(U, W)| = |K| -> 0 inherits the rounding residue of j5
+        // (itself next to a double root there: 1 - arg5 ~ K^2 / 2C^2) amplified by C^2 / K^2: below |K| = 2e-5 (joint 4
+        // within 6e-5 rad of 2.63084 or 0) that reaches 1e-8 rad and more, enough to move the shoulder's duplicate-root
+        // and singular-branch tests -- seen on the GPU as one count mismatch in 12 M structured solves.
+        if (near_threshold(fabs(q0), kBranchThresh) || near_threshold(fabs(U) + fabs(W), kBranchThresh) || fabs(K) < 2e-5)
             out.status |= kStatusIllConditioned;
         if (fabs(q0) < kBranchThresh || fabs(U) + fabs(W) < kBranchThresh || fabs(sK) < kBranchThresh) {
             // Elbow singularity: K = 0, the shoulder centre lies on the forearm (joint-5) axis, so the position
