@@ -66,9 +66,15 @@ def main():
     per = max(D.shard_bounds(E, r, world)[1] - D.shard_bounds(E, r, world)[0] for r in range(world))
     buf = D.PeerIndexBuffer(per)
     a_blk, b_blk = a[:, lo:hi].contiguous(), b[:, lo:hi].contiguous()
-    ms_p2p = timed(lambda: buf.edge_feasibility(a_blk, b_blk, W, 5.0, mode="rne"))
-    buf.edge_feasibility(a_blk, b_blk, W, 5.0, mode="rne")
-    buf.barrier()
+    # like for like with the NCCL form (which pays for its synchronisation inside the collective): every step publishes
+    # its completion and waits for every rank's (tcmp_peer_signal / tcmp_peer_wait on the buffer's side stream), and the
+    # step ends when this rank holds every rank's block
+    def fused_step():
+        buf.edge_feasibility(a_blk, b_blk, W, 5.0, mode="rne", overlap_gather=True)
+        buf.join()
+    ms_p2p = timed(fused_step)
+    fused_step()
+    torch.cuda.synchronize()
     got = torch.cat([buf.gathered[r, : D.shard_bounds(E, r, world)[1] - D.shard_bounds(E, r, world)[0]] for r in range(world)])
     assert torch.equal(got, single), "peer-store gather != single-GPU first_fail"
     if rank == 0:
