@@ -320,6 +320,15 @@ int tcmp_rne_batch_host(tcmp_workspace *ws, int mode, int dtype, int64_t n, cons
                         const void *qd, const void *qdd, const void *payload_mass,
                         double payload_scalar, double payload_threshold, void *tau_out,
                         uint8_t *feasible_out);
+/* The same call without the final wait: it enqueues the whole chunk pipeline on the workspace's streams and returns.
+ * Consecutive calls on one workspace pipeline across batches (the host->device copies of batch i + 1 run while batch
+ * i's last chunk is still computing and reading back); the output arrays of a batch are complete -- and its input
+ * arrays may be reused -- after tcmp_workspace_sync.  Host arrays must be pinned for the overlap to happen. */
+int tcmp_rne_batch_host_async(tcmp_workspace *ws, int mode, int dtype, int64_t n, const void *q,
+                        const void *qd, const void *qdd, const void *payload_mass,
+                        double payload_scalar, double payload_threshold, void *tau_out,
+                        uint8_t *feasible_out);
+int tcmp_workspace_sync(tcmp_workspace *ws);
 int tcmp_edge_feasibility_host(tcmp_workspace *ws, int mode, int dtype, int64_t n_edges,
                                int n_waypoints, const void *qa, const void *qb,
                                double payload_scalar, double payload_threshold, int static_only,

@@ -164,6 +164,27 @@ def test_host_path_matches_device_path(eng):
     ws.close()
 
 
+def test_async_host_batches_pipeline_and_match(eng):
+    """tcmp_rne_batch_host_async: three batches enqueued back to back on one workspace (pinned arrays, distinct
+    outputs), one tcmp_workspace_sync -- every batch equals the synchronous call bit for bit."""
+    import torch
+    ws = eng.Workspace(chunk_states=1 << 15)
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory().numpy()
+    batches, outs = [], []
+    for b in range(3):
+        q, qd, qdd, mass = (pin(a) for a in sample_states(100_003 + 17 * b, seed=40 + b))
+        tau = pin(np.empty_like(q))
+        ok = pin(np.empty(q.shape[1], dtype=np.uint8))
+        eng.torque_test_batch_host_async(ws, "rne", "f64", q, qd, qdd, mass, 0.0, 0.01, tau, ok)
+        batches.append((q, qd, qdd, mass))
+        outs.append((tau, ok))
+    eng.workspace_sync(ws)
+    for (q, qd, qdd, mass), (tau, ok) in zip(batches, outs):
+        tau_s, ok_s = eng.torque_test_batch(q, qd, qdd, mass, mode="rne", workspace=ws)
+        assert np.array_equal(tau, tau_s) and np.array_equal(ok, ok_s)
+    ws.close()
+
+
 def test_payload_affinity_property_1m(eng):
     """Size-independent property at the BASELINE size (1M states): the torque is affine in the payload
     mass (the payload link's inertia is linear in m, rne.py:85-100), so tau(5) - tau(0) == 5 (tau(1) - tau(0));

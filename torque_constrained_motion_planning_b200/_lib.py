@@ -62,6 +62,8 @@ SIGNATURES = {
     "tcmp_workspace_create": (_i32, [ctypes.POINTER(_vp), _i64]),
     "tcmp_workspace_destroy": (_i32, [_vp]),
     "tcmp_rne_batch_host": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _vp]),
+    "tcmp_rne_batch_host_async": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _vp]),
+    "tcmp_workspace_sync": (_i32, [_vp]),
     "tcmp_edge_feasibility_host": (_i32, [_vp, _i32, _i32, _i64, _i32, _vp, _vp, _f64, _f64, _i32, _vp]),
     "tcmp_ik_batch_host": (_i32, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "tcmp_host_alloc": (_i32, [ctypes.POINTER(_vp), _i64]),

@@ -499,9 +499,34 @@ static int64_t next_chunk(int64_t remaining, int64_t C) {
     return remaining;
 }
 
+static int rne_batch_host_impl(tcmp_workspace *ws, int mode, int dtype, int64_t n, const void *q, const void *qd,
+                               const void *qdd, const void *payload_mass, double payload_scalar,
+                               double payload_threshold, void *tau_out, uint8_t *feasible_out, bool drain);
+
 int tcmp_rne_batch_host(tcmp_workspace *ws, int mode, int dtype, int64_t n, const void *q, const void *qd,
                         const void *qdd, const void *payload_mass, double payload_scalar, double payload_threshold,
                         void *tau_out, uint8_t *feasible_out) {
+    return rne_batch_host_impl(ws, mode, dtype, n, q, qd, qdd, payload_mass, payload_scalar, payload_threshold, tau_out,
+                               feasible_out, true);
+}
+
+int tcmp_rne_batch_host_async(tcmp_workspace *ws, int mode, int dtype, int64_t n, const void *q, const void *qd,
+                              const void *qdd, const void *payload_mass, double payload_scalar,
+                              double payload_threshold, void *tau_out, uint8_t *feasible_out) {
+    return rne_batch_host_impl(ws, mode, dtype, n, q, qd, qdd, payload_mass, payload_scalar, payload_threshold, tau_out,
+                               feasible_out, false);
+}
+
+int tcmp_workspace_sync(tcmp_workspace *ws) {
+    if (!ws) return fail(TCMP_ERR_INVALID_ARG, "workspace is NULL");
+    DeviceScope scope(ws->device);
+    TCMP_CUDA(ws_drain(ws));
+    return TCMP_OK;
+}
+
+static int rne_batch_host_impl(tcmp_workspace *ws, int mode, int dtype, int64_t n, const void *q, const void *qd,
+                               const void *qdd, const void *payload_mass, double payload_scalar,
+                               double payload_threshold, void *tau_out, uint8_t *feasible_out, bool drain) {
     if (!ws) return fail(TCMP_ERR_INVALID_ARG, "workspace is NULL");
     DeviceScope scope(ws->device);
     if (int rc = check_common(mode, dtype, n)) return rc;
@@ -537,7 +562,7 @@ int tcmp_rne_batch_host(tcmp_workspace *ws, int mode, int dtype, int64_t n, cons
         if (tau_out) TCMP_CUDA_WS(ws, d2h_rows(tau_out, dtau, 7, n, off, len, esz, st));
         if (feasible_out) TCMP_CUDA_WS(ws, d2h_rows(feasible_out, dmask, 1, n, off, len, 1, st));
     }
-    TCMP_CUDA(ws_drain(ws));
+    if (drain) TCMP_CUDA(ws_drain(ws));
     return TCMP_OK;
 }
 

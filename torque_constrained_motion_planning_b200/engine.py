@@ -235,6 +235,22 @@ def torque_test_batch_host_into(ws: Workspace, mode, dtype, q, qd, qdd, payload_
                                          _nptr(tau_out), _nptr(mask_out)))
 
 
+def torque_test_batch_host_async(ws: Workspace, mode, dtype, q, qd, qdd, payload_mass, payload_scalar,
+                                 payload_threshold, tau_out, mask_out) -> None:
+    """tcmp_rne_batch_host_async: enqueue one batch of pinned host arrays and return; consecutive batches pipeline on the
+    workspace's streams.  Outputs are complete (and inputs reusable) after ``workspace_sync(ws)``."""
+    n = int(q.shape[1])
+    with ws.lock:
+        check(load().tcmp_rne_batch_host_async(ws.handle, MODE[mode], DTYPE[dtype], n, _nptr(q), _nptr(qd), _nptr(qdd),
+                                               _nptr(payload_mass), float(payload_scalar), float(payload_threshold),
+                                               _nptr(tau_out), _nptr(mask_out)))
+
+
+def workspace_sync(ws: Workspace) -> None:
+    with ws.lock:
+        check(load().tcmp_workspace_sync(ws.handle))
+
+
 def edge_feasibility(qa, qb, n_waypoints: int = 64, payload_mass: float = 0.0, mode: str = "rne",
                      dtype: str = "f64", payload_threshold: float = PAYLOAD_THRESHOLD_TEST,
                      static_only: bool = False, workspace: Optional[Workspace] = None,
