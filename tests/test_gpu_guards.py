@@ -79,6 +79,66 @@ def test_output_guard_bands(n):
     assert 0 <= int(first.item()) <= ns
 
 
+@pytest.mark.parametrize("n", [1, 33, 1000, 20011])
+def test_round2_kernels_guard_bands(n):
+    """The kernels added in round 2, same own-bounds-check scheme: the IK redo pass (every pose at the elbow
+    singularity, so the second kernel writes all solution sets), the BASE-mode trajectory, the scatter kernel with a
+    destination offset, tcmp_peer_push, and the completion-flag kernels on a sync block."""
+    import ctypes
+    import torch
+    from torque_constrained_motion_planning_b200 import _lib, min_jerk_v2
+    lib = _lib.load()
+    st = int(torch.cuda.current_stream().cuda_stream)
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+    qh, qdh, qddh, mh = sample_states(n, seed=100 + n)
+    qh[3] = 2.63084142381503
+    qh[3, ::3] = 0.0
+    q, qd, qdd, m = (dev(a) for a in (qh, qdh, qddh, mh))
+    b1, trans, s1 = guarded(torch, (3, n), torch.float64)
+    b2, rot, s2 = guarded(torch, (9, n), torch.float64)
+    _lib.check(lib.tcmp_fk_batch(n, q.data_ptr(), trans.data_ptr(), rot.data_ptr(), st))
+    nf = 2
+    free = dev(np.vstack([qh[6:7], np.zeros((1, n))]))
+    b3, sols, s3 = guarded(torch, (n * nf, 8, 7), torch.float64)
+    b4, cnt, s4 = guarded(torch, (n * nf,), torch.int32)
+    b5, stat, s5 = guarded(torch, (n * nf,), torch.uint8)
+    _lib.check(lib.tcmp_ik_batch(n, rot.data_ptr(), trans.data_ptr(), free.data_ptr(), nf, 0, sols.data_ptr(),
+                                 cnt.data_ptr(), stat.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert intact(b3, n * nf * 56, s3) and intact(b4, n * nf, s4) and intact(b5, n * nf, s5)
+    assert bool(((cnt >= 0) & (cnt <= 8)).all()) and bool((sols != s3).all()) and bool((stat < 16).all())
+    assert int((stat & 1).sum()) >= n // 2            # the elbow branch (and with it the redo kernel) was taken
+    # BASE-mode trajectory: samples and torques written, mask all 1
+    pts = np.random.default_rng(n).uniform(Q_LO, Q_HI, size=(4, 7))
+    coeffs = dev(min_jerk_v2.coefficients_for_kernel(min_jerk_v2.minjerk_coefficients(pts)))
+    S = max(1, n // 3)
+    ns = 3 * S
+    outs = [guarded(torch, (7, ns), torch.float64) for _ in range(4)]
+    bk, msk, sk = guarded(torch, (ns,), torch.uint8)
+    first = torch.full((1,), ns, dtype=torch.int32, device="cuda")
+    _lib.check(lib.tcmp_traj_feasibility(3, 0, 3, S, coeffs.data_ptr(), 5.0, 0.01, outs[0][1].data_ptr(),
+                                         outs[1][1].data_ptr(), outs[2][1].data_ptr(), outs[3][1].data_ptr(),
+                                         msk.data_ptr(), first.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert all(intact(b, 7 * ns, s) for b, _, s in outs) and intact(bk, ns, sk)
+    assert all(bool((o != s).all()) for _, o, s in outs) and bool((msk == 1).all()) and int(first.item()) == ns
+    # scatter into row 1 of a [3][n] gathered buffer, push into row 2; rows 0 and the guard bands stay untouched
+    bg, gathered, sg = guarded(torch, (3, n), torch.uint8)
+    ptrs = (ctypes.c_void_p * 1)(gathered.data_ptr())
+    bt, tau, s_t = guarded(torch, (7, n), torch.float64)
+    _lib.check(lib.tcmp_rne_batch_scatter(0, 0, n, q.data_ptr(), qd.data_ptr(), qdd.data_ptr(), m.data_ptr(), 0.0, 0.01,
+                                          tau.data_ptr(), 1, ptrs, n, st))
+    _lib.check(lib.tcmp_peer_push(gathered[1].data_ptr(), n, 1, ptrs, 2 * n, st))
+    sync = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    sptrs = (ctypes.c_void_p * 1)(sync.data_ptr())
+    _lib.check(lib.tcmp_peer_signal(0, 1, sptrs, st))
+    _lib.check(lib.tcmp_peer_wait(sync.data_ptr(), 1, st))
+    torch.cuda.synchronize()
+    assert intact(bg, 3 * n, sg) and intact(bt, 7 * n, s_t) and bool((gathered[0] == sg).all())
+    assert bool((gathered[1] <= 1).all()) and torch.equal(gathered[1], gathered[2])
+    assert int(sync.view(torch.int64)[0]) == 1 and int(sync.view(torch.int64)[8]) == 1   # arrived[0] = epoch = 1
+
+
 def test_concurrent_host_calls_share_the_default_workspace():
     """Python threads calling the host-array entry points at once: the shared default workspace is serialised by
     its lock, device calls on per-thread streams need none.  Every thread must get its own inputs' results."""
