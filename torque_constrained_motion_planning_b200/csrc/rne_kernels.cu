@@ -133,7 +133,10 @@ rne_batch_kernel(I n, const T *__restrict__ q, const T *__restrict__ qd, const T
     // Register double buffering: the NEXT grid-stride state's 22 inputs are loaded before the current state's
     // recursion starts, so a warp never sits in a long-scoreboard stall with nothing to issue (ncu: 1.06 -> 0.14
     // long-scoreboard stalls per issue).  (Ping-ponging two register sets instead of copying next -> current spills
-    // and is 16 % slower; prefetch.global of the next rows costs 76 registers and 9 % -- see DESIGN.md 6b.)
+    // and is 16 % slower; prefetch.global of the next rows costs 76 registers and 9 % -- see DESIGN.md 6b.  Round 2:
+    // staging the next state in shared memory with cp.async instead -- 125 registers, 4 CTAs / SM, no spills -- is 3 %
+    // SLOWER (22.1 vs 22.8 G states/s burst): more resident warps do not help a kernel whose sustained rate is set by
+    // the 1 kW power cap, profiles/r02/k1_variants.log.)
     const I stride = (I)(gridDim.x * blockDim.x);
     I i = (I)(blockIdx.x * blockDim.x + threadIdx.x);
     const bool any = i < n;
