@@ -79,7 +79,9 @@ def test_config3_one_million_poses_times_25(eng):
     mism = np.nonzero(c != counts_ref)[0]
     assert len(mism) == 0, (len(mism), mism[:10], c[mism[:10]], counts_ref[mism[:10]])
     assert (c.reshape(n, nf)[:, 0] >= 1).all()
-    assert int((status & 0xf7).max()) == 0 and int((status & 8 != 0).sum()) <= 10   # bit 3: within 1 % of a threshold
+    # bit 3 (ill-conditioned: a test within 1 % of its threshold, or joint 4 within 6e-5 rad of the elbow singularity)
+    # is allowed on at most 1e-5 of the random solves; no other bit
+    assert int((status & 0xf7).max()) == 0 and int((status & 8 != 0).sum()) <= 250
     m = 20_000
     sols, _, _ = eng.ik_batch(rot[:, :m].contiguous(), trans[:, :m].contiguous(), dev(free[:, :m]))
     sols_ref, cr = oracle.ref_ik_batch(rot_h[:, :m], trans_h[:, :m], free[:, :m], nthreads=NT)
