@@ -61,3 +61,41 @@ def test_committed_bench_evidence_follows_the_contract():
             assert abs(d["value"] - 1e6 * d["steps"] / (d["ms_per_step"] * d["steps"] * 1e-3)) / d["value"] < 1e-6
     ref = json.loads(open(os.path.join(prof, "bench_reference_n1_final.json")).read())
     assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["config"]["workload"] == d["config"]["workload"]
+
+
+def test_round2_bench_evidence_follows_the_contract():
+    """profiles/r02: the final build's driver-command lines.  Beyond the round-1 keys: `launch` (one CUDA graph), `settle`,
+    `sustained` as a first-class key, `roofline.traffic` read from the committed ncu CSV, the executed FP64 count, the
+    planner extras with a MEASURED reference time, the host-link ceiling, and a reference arm within 10 % of the GPU arm's
+    cpu_baseline on the same box (VERDICT r01 #2)."""
+    prof = os.path.join(ROOT, "profiles", "r02")
+    d = json.loads(open(os.path.join(prof, "bench_n1_final.json")).read())
+    ref = json.loads(open(os.path.join(prof, "bench_reference_n1_final.json")).read())
+    assert d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] >= 3 and d["gpu_launches"] == 20
+    assert d["launch"].startswith("one CUDA graph") and d["settle"]["seconds"] > 0
+    assert abs(d["value"] - 1e6 * d["steps"] / (d["ms_per_step"] * d["steps"] * 1e-3)) / d["value"] < 1e-6
+    assert abs(d["sustained"]["value"] / d["value"] - 1) < 0.05          # same clock regime: K = 20 agrees with 1.5 s
+    r = d["roofline"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic_source"].startswith("profiles/r02/")
+    assert 150e6 < r["traffic"] <= 233e6 and r["executed"]["fp64_instr_per_state"] <= 600
+    assert 0.5 < r["executed"]["pipe_frac"] < r["frac"] <= 1.0
+    assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["config"]["workload"] == d["config"]["workload"]
+    assert abs(ref["value"] / d["cpu_baseline"]["value"] - 1) < 0.10 and ref["cpu_baseline"]["cores"] == d["cpu_baseline"]["cores"]
+    e = d["e2e"]
+    assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] == 176_000_000 and e["d2h_bytes_per_step"] == 57_000_000
+    assert 0.8 < e["link"]["in_call_share_of_ceiling"] <= 1.2 and e["pipelined"]["value"] > e["value"]
+    for p in d["extras"]["planner"]:
+        assert p["gpu_strict_trajectory_equals_reference"] is True and p["reference_measured_s"] > 20
+        assert p["gpu_strict_s"] < 0.2 and p["gpu_batched_s"] < p["gpu_strict_s"]
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert not bad & set(d["clocks"]["reasons"])
+    values = {}
+    for n in (1, 2, 4, 8):
+        s = json.loads([l for l in open(os.path.join(prof, "scale_n%d.json" % n)) if l.startswith("{")][-1])
+        assert s["n_gpus"] == n and s["scaling"] == "weak" and s["launch"].startswith("one CUDA graph")
+        assert s["gpu_launches"] == (20 if n == 1 else 60)            # N > 1: scatter kernel + signal + wait per step
+        if n > 1:
+            assert s["gather_check"].startswith("peer-store gather") and "tcmp_peer_signal" in s["gather"]
+        assert 0.8 < s["e2e"]["link"]["in_call_share_of_ceiling"] <= 1.2
+        values[n] = s["value"]
+    assert values[8] / (8 * values[1]) > 0.90 and values[2] / (2 * values[1]) > 0.95
