@@ -660,6 +660,7 @@ def main():
         refm = torch.empty((world, N_STATES), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(refm, mine)
         assert torch.equal(refm, got), "peer-store gather != NCCL all-gather"
+        peer.check()              # no tcmp_peer_wait of this run gave up on a rank
         gather_check = "peer-store gather + device-side wait == NCCL all_gather_into_tensor"
 
     # ---- the other hot-path workloads (BASELINE.json configs[0], [2], [3], [4]); single-GPU runs only -------

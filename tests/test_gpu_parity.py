@@ -346,7 +346,7 @@ def test_scatter_kernel_single_rank(eng):
         assert np.array_equal(got.cpu().numpy(), ok_o)
     buf.torque_test(dev(q[:, :0]), dev(qd[:, :0]), dev(qdd[:, :0]), dev(mass[:0]), want_tau=False, overlap_gather=True)
     buf.join()
-    torch.cuda.synchronize()
+    buf.check()              # synchronises; raises if a wait kernel had timed out
     seen = seen[:4]
     # consecutive steps cycle through the three copies of the gathered buffer (read -> next-write ordering)
     assert len(set(seen[:3])) == 3 and seen[0] == seen[3]

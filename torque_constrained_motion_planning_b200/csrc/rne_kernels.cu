@@ -327,14 +327,21 @@ __global__ void peer_signal_kernel(SyncDests d) {
 
 // Consumer side: lane r waits until rank r has published an epoch >= this rank's own (every rank runs the same
 // sequence of scatter steps, so epochs line up); acquire loads at system scope, back-off while spinning.
+// A peer that died never publishes: after ~20 s of polling the lane gives up and records it in the sync block
+// (pad[0] = 1 + the rank it waited for; PeerMaskBuffer.check() raises on it) instead of hanging the GPU.
 __global__ void peer_wait_kernel(PeerSync *own, int world) {
     const unsigned long long e = own->epoch;
     if ((int)threadIdx.x < world) {
         const unsigned long long *flag = &own->arrived[threadIdx.x];
         unsigned long long v;
+        const long long t0 = clock64();
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
             if (v >= e) break;
+            if (clock64() - t0 > 40000000000ll) {          // ~20 s at 2 GHz
+                own->pad[0] = 1u + threadIdx.x;
+                break;
+            }
             __nanosleep(200);
         }
     }

@@ -329,6 +329,15 @@ class PeerMaskBuffer:
         self._done[step] = done
         self._done.pop(step - self.SLOTS, None)
 
+    def check(self):
+        """Synchronise and raise if a tcmp_peer_wait gave up on a rank (~20 s without its epoch: that rank is gone)."""
+        import torch
+        torch.cuda.synchronize()
+        word = torch.as_tensor(_DevArray(self._sync_own.value, 128, "|u1"),
+                               device=torch.device("cuda", torch.cuda.current_device())).view(torch.int32)[19]
+        if int(word.item()) != 0:
+            raise RuntimeError("tcmp_peer_wait timed out waiting for rank %d" % (int(word.item()) - 1))
+
     def join(self):
         """Current stream waits until the last step's gather is complete on this rank."""
         import torch
