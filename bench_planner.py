@@ -6,8 +6,10 @@
   * cpu_serial   : the SAME planner code with the torque predicate replaced by the CPU oracle called ONE STATE AT
                    A TIME and the NumPy collision stand-in -- the reference planner's structure
                    (rrt_star.py:90-98,203-210) with a torque test ~400x faster than the reference's rne.py
-  * python_reference_estimate : cpu_serial's torque-call count x 2.6 ms (rne.py per call)
-                   + the 2nd logging sweep the reference makes in Conf.__init__ (utils.py:3376-3378)
+  * reference_measured_s : the reference's OWN planner loop (rrt_star_force_aware + rne.rne + min_jerk_v2 + IKFast,
+                   NumPy collision twin, the Conf.__init__ logging sweep included), measured once in the CPU container by
+                   scripts/reference_planner_cpu.py with the same seed / scene / start / target and committed as
+                   profiles/r02/reference_planner_cpu.json (round 1 quoted an estimate: calls x 2.6 ms)
 
 PyBullet and the reference's scene code are out of scope: all arms use the synthetic scene of
 collision.py and the same seeds.  One JSON line per scene.
@@ -102,14 +104,21 @@ def main():
         same = (traj is not None and out_cpu is not None and
                 np.array(out_cpu[0]).shape == (len(traj.path), 7) and
                 np.allclose(np.array([c_.values for c_ in traj.path]), np.array(out_cpu[0]), rtol=0, atol=1e-12))
+        try:
+            ref = {r["scene"]: r for r in json.load(open(os.path.join(ROOT, "profiles", "r02",
+                                                                      "reference_planner_cpu.json")))["results"]}.get(name)
+        except Exception:
+            ref = None
+        ref_s = None if ref is None else ref["reference_measured_s"]
         print(json.dumps({
             "scene": name, "samples": None if traj is None else len(traj.path),
             "gpu_strict_s": t_strict, "gpu_batched_s": t_batched, "gpu_batched_arrays_s": t_arrays,
             "gpu_batched_samples": None if traj_b is None else len(traj_b.path),
             "cpu_serial_s": t_cpu, "cpu_torque_calls": n_calls,
-            "python_reference_estimate_s": n_calls * 2.6e-3,
+            "reference_measured_s": ref_s, "reference_rne_calls": None if ref is None else ref["rne_calls"],
             "gpu_strict_path_equals_cpu_serial_path": bool(same),
-            "speedup_vs_cpu_serial": t_cpu / t_strict, "speedup_vs_python_reference_estimate": n_calls * 2.6e-3 / t_strict,
+            "speedup_vs_cpu_serial": t_cpu / t_strict,
+            "speedup_vs_reference_measured": None if ref_s is None else ref_s / t_strict,
         }))
 
 
