@@ -27,17 +27,16 @@ namespace ik {
 // coalesced 256 B stores -- instead of 56 scattered 8 B stores per lane that each dirty their own 32 B sector.
 constexpr int kSolRow = 57;
 
-constexpr int kIkBlock = 64;   // 2 warps x 32 rows x 57 doubles = 29 KB of static shared memory (< 48 KB)
 
-// Compacting kernel.  (The first build mapped one lane to one solve for its whole life; ncu showed 14 of 32 lanes
-// active, because ~45 % of a sweep's solves fail the solver's first gate and return at once while their warp-mates
-// run all 8 branches -- profiles/r01/ncu_full_ik_kernel_raw.csv.)  Each warp walks chunks of 32
-// consecutive solves; lanes SCREEN their solve (pose reduction + the j3 gate), finish the rejected ones on the spot
-// and push the survivors' indices into a per-warp shared-memory queue (ballot / popc prefix).  Whenever 32
-// survivors are queued, the warp solves them with every lane busy.  Solution sets are staged in shared memory and
-// written row by row with coalesced stores.
-constexpr int kQueueCap = 64;   // <= 31 left over + 32 pushed per chunk
-
+// Compacting kernel, CTA-wide (round 2).  History: one lane per solve for its whole life ran with 14 of 32 lanes active
+// (~45 % of a sweep's solves fail the solver's first gate and return at once while their warp-mates run all 8
+// branches); per-WARP survivor queues brought that to 20 and 3.3 G solves/s, but every warp then sat at its own program
+// counter in ~100 KB of inlined solver code and the kernel stalled on instruction fetch (ncu: 1.1 "no instruction"
+// stalls per issue, 2.1 with solution sets).  Now ONE large CTA per SM: every iteration all lanes screen one solve each
+// (pose reduction + the j3 gate), survivors are appended to ONE shared-memory queue (block-level prefix over the warps'
+// ballots), and whenever the queue holds a CTA's worth of entries ALL warps solve at the same time -- they walk the
+// solver's code together, so one instruction fetch serves them all: 4.3 G solves/s counts only (+28 %).  Solution sets
+// are staged in (dynamic) shared memory, one padded row per lane, and written row by row with coalesced stores.
 __device__ __forceinline__ void load_pose(int64_t s, int64_t n, int n_free, int free_broadcast,
                                           const double *__restrict__ rot9, const double *__restrict__ trans3,
                                           const double *__restrict__ free_vals, Pose &P) {
@@ -50,100 +49,104 @@ __device__ __forceinline__ void load_pose(int64_t s, int64_t n, int n_free, int 
     prepare_pose(R, __ldg(trans3 + p), __ldg(trans3 + n + p), __ldg(trans3 + 2 * n + p), j6, P);
 }
 
-#ifndef TCMP_IK_MINBLOCKS
-#define TCMP_IK_MINBLOCKS 1
-#endif
-template <bool WRITE_SOLS>
-__global__ void __launch_bounds__(kIkBlock, TCMP_IK_MINBLOCKS)
-ik_kernel_compact(int64_t n, int n_free, int free_broadcast, const double *__restrict__ rot9,
-                  const double *__restrict__ trans3, const double *__restrict__ free_vals,
-                  double *__restrict__ sols_out, int32_t *__restrict__ count_out, uint8_t *__restrict__ status_out) {
-    __shared__ double stage[WRITE_SOLS ? (kIkBlock / 32) * 32 * kSolRow : 1];
-    __shared__ long long queue_all[kIkBlock / 32][kQueueCap];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    long long *queue = queue_all[wib];
-    double *rows = &stage[WRITE_SOLS ? wib * 32 * kSolRow : 0];
+template <int THREADS, bool WRITE_SOLS>
+__global__ void __launch_bounds__(THREADS, 1)
+ik_kernel_cta(int64_t n, int n_free, int free_broadcast, const double *__restrict__ rot9,
+              const double *__restrict__ trans3, const double *__restrict__ free_vals,
+              double *__restrict__ sols_out, int32_t *__restrict__ count_out, uint8_t *__restrict__ status_out) {
+    constexpr int kWarps = THREADS / 32;
+    extern __shared__ double rows[];                 // WRITE_SOLS: [THREADS][kSolRow]
+    __shared__ long long queue[2 * THREADS];         // <= THREADS - 1 left over + THREADS pushed per iteration
+    __shared__ int warp_cnt[kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t total = n * n_free;
-    const int64_t n_chunks = (total + 31) / 32;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    int qn = 0;   // warp-uniform queue length
-
-    auto solve_batch = [&](int cnt) {   // the first `cnt` queue entries, one per lane
-        long long s = -1;
-        if (lane < cnt) {
-            s = queue[lane];
-            Pose P;
-            load_pose(s, n, n_free, free_broadcast, rot9, trans3, free_vals, P);
-            Emit out;
-            out.sols = WRITE_SOLS ? rows + lane * kSolRow : nullptr;
-            out.count = 0;
-            out.status = 0;
-            solve_one_t<false>(P, out);
-            // elbow singularity: ik_redo_kernel finishes this solve with the complete tree (keeping that tree out of
-            // this kernel keeps it at 128 / 150 registers instead of 168)
-            const bool redo = (out.status & kStatusRedo) != 0;
-            if (redo) out.count = 0;
-            if (WRITE_SOLS)
-                for (int k = (out.count < 8 ? out.count : 8) * 7; k < 56; ++k) rows[lane * kSolRow + k] = 0.0;
-            count_out[s] = redo ? -1 : out.count;
-            if (status_out) status_out[s] = (uint8_t)out.status;
-        }
-        if (WRITE_SOLS) {
-            __syncwarp();
-            for (int r = 0; r < cnt; ++r) {   // row r -> its solve's 448 B slot: two coalesced stores per row
-                double *dst = sols_out + queue[r] * 56;
-                dst[lane] = rows[r * kSolRow + lane];
-                if (lane < 24) dst[32 + lane] = rows[r * kSolRow + 32 + lane];
-            }
-            __syncwarp();
-        }
-    };
-
-    for (int64_t c = warp; c < n_chunks; c += n_warps) {
-        const int64_t s = c * 32 + lane;
+    const int64_t per_iter = (int64_t)gridDim.x * THREADS;
+    const int64_t n_iter = (total + per_iter - 1) / per_iter;     // the same trip count for every thread (barriers inside)
+    int qn = 0;                                                   // CTA-uniform queue length
+    for (int64_t it = 0; it <= n_iter; ++it) {
+        const bool last = it == n_iter;                           // one extra pass drains the queue
         bool go = false, dead = false;
-        if (s < total) {
-            Pose P;
-            load_pose(s, n, n_free, free_broadcast, rot9, trans3, free_vals, P);
-            const int verdict = screen_pose(P);
-            go = verdict == 1;
-            dead = !go;
-            if (dead) {
-                count_out[s] = 0;
-                if (status_out) status_out[s] = (uint8_t)(verdict == 2 ? kStatusInvalid : 0);
+        long long s = -1;
+        if (!last) {
+            s = (it * gridDim.x + blockIdx.x) * THREADS + tid;
+            if (s < total) {
+                Pose P;
+                load_pose(s, n, n_free, free_broadcast, rot9, trans3, free_vals, P);
+                const int verdict = screen_pose(P);
+                go = verdict == 1;
+                dead = !go;
+                if (dead) {
+                    count_out[s] = 0;
+                    if (status_out) status_out[s] = (uint8_t)(verdict == 2 ? kStatusInvalid : 0);
+                }
             }
         }
-        const unsigned m_go = __ballot_sync(0xffffffffu, go);
-        if (go) queue[qn + __popc(m_go & lt_mask)] = s;
-        qn += __popc(m_go);
-        if (WRITE_SOLS) {   // zero-fill the rejected solves' slots, row by row, coalesced
+        const unsigned m = __ballot_sync(0xffffffffu, go);
+        if (lane == 0) warp_cnt[wib] = __popc(m);
+        if (WRITE_SOLS) {   // zero-fill the rejected solves' slots: each warp its own 32 consecutive solves, coalesced
             unsigned m_dead = __ballot_sync(0xffffffffu, dead);
+            const long long s0 = s - lane;                        // the warp's first solve of this iteration
             while (m_dead) {
                 const int r = __ffs(m_dead) - 1;
                 m_dead &= m_dead - 1;
-                double *dst = sols_out + (c * 32 + r) * 56;
+                double *dst = sols_out + (__shfl_sync(0xffffffffu, s0, 0) + r) * 56;
                 dst[lane] = 0.0;
                 if (lane < 24) dst[32 + lane] = 0.0;
             }
         }
-        __syncwarp();
-        if (qn >= 32) {
-            solve_batch(32);
-            const int rest = qn - 32;
+        __syncthreads();
+        int before = 0, added = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const int cw = warp_cnt[w];
+            if (w < wib) before += cw;
+            added += cw;
+        }
+        if (go) queue[qn + before + __popc(m & lt_mask)] = s;
+        qn += added;
+        __syncthreads();
+        const int take = last ? qn : (qn >= THREADS ? THREADS : 0);     // CTA-uniform
+        if (take > 0) {
+            if (tid < take) {
+                const long long sq = queue[tid];
+                Pose P;
+                load_pose(sq, n, n_free, free_broadcast, rot9, trans3, free_vals, P);
+                Emit out;
+                out.sols = WRITE_SOLS ? rows + tid * kSolRow : nullptr;
+                out.count = 0;
+                out.status = 0;
+                solve_one_t<false>(P, out);
+                // elbow singularity: ik_redo_kernel finishes this solve with the complete tree (keeping that tree out
+                // of this kernel keeps its registers down)
+                const bool redo = (out.status & kStatusRedo) != 0;
+                if (redo) out.count = 0;
+                if (WRITE_SOLS)
+                    for (int k = (out.count < 8 ? out.count : 8) * 7; k < 56; ++k) rows[tid * kSolRow + k] = 0.0;
+                count_out[sq] = redo ? -1 : out.count;
+                if (status_out) status_out[sq] = (uint8_t)out.status;
+            }
+            if (WRITE_SOLS) {
+                __syncthreads();
+                for (int r = wib; r < take; r += kWarps) {   // row r -> its solve's 448 B slot: two coalesced stores
+                    double *dst = sols_out + queue[r] * 56;
+                    dst[lane] = rows[r * kSolRow + lane];
+                    if (lane < 24) dst[32 + lane] = rows[r * kSolRow + 32 + lane];
+                }
+            }
+            const int rest = qn - take;
             long long carry = 0;
-            if (lane < rest) carry = queue[32 + lane];
-            __syncwarp();
-            if (lane < rest) queue[lane] = carry;
-            __syncwarp();
+            __syncthreads();
+            if (tid < rest) carry = queue[take + tid];
+            __syncthreads();
+            if (tid < rest) queue[tid] = carry;
             qn = rest;
+            __syncthreads();
         }
     }
-    if (qn > 0) solve_batch(qn);
 }
 
-// Second pass of tcmp_ik_batch: the solves ik_kernel_compact marked with count = -1 (elbow singularity met on the hot
+// Second pass of tcmp_ik_batch: the solves ik_kernel_cta marked with count = -1 (elbow singularity met on the hot
 // path) are redone with the complete decision tree.  One lane per solve; the scan reads 4 B per solve (25 M solves:
 // 100 MB, ~20 us), the flagged solves are rare outside hand-built singular sweeps.
 template <bool WRITE_SOLS>
@@ -211,20 +214,34 @@ fk_kernel(int64_t n, const double *__restrict__ q, double *__restrict__ trans3, 
 
 }  // namespace ik
 
+// counts only: 512 threads (128 registers, one CTA per SM); with solution sets the padded rows need 57 doubles of shared
+// memory per lane: 384 threads = 171 KB of the SM's 227 KB
+constexpr int kIkThreadsCounts = 512;
+constexpr int kIkThreadsSets = 384;
+
 cudaError_t launch_ik_batch(int64_t n, const double *rot9, const double *trans3, const double *free_vals,
                             int n_free, int free_broadcast, double *sols_out, int32_t *count_out,
                             uint8_t *status_out, cudaStream_t st) {
     if (sols_out) {
-        const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel_compact<true>), ik::kIkBlock, n * n_free);
-        ik::ik_kernel_compact<true><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals,
-                                                                   sols_out, count_out, status_out);
+        auto kern = ik::ik_kernel_cta<kIkThreadsSets, true>;
+        const size_t smem = (size_t)kIkThreadsSets * ik::kSolRow * sizeof(double);
+        static bool configured[64] = {};      // per device: opt in to > 48 KB of dynamic shared memory once
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 64 && !configured[dev]) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured[dev] = true;
+        }
+        kern<<<sm_count(), kIkThreadsSets, smem, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out,
+                                                       count_out, status_out);
         const int grid2 = grid_for(reinterpret_cast<const void *>(ik::ik_redo_kernel<true>), 128, n * n_free);
         ik::ik_redo_kernel<true><<<grid2, 128, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out,
                                                         count_out, status_out);
     } else {
-        const int grid = grid_for(reinterpret_cast<const void *>(ik::ik_kernel_compact<false>), ik::kIkBlock, n * n_free);
-        ik::ik_kernel_compact<false><<<grid, ik::kIkBlock, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals,
-                                                                    sols_out, count_out, status_out);
+        ik::ik_kernel_cta<kIkThreadsCounts, false><<<sm_count(), kIkThreadsCounts, 0, st>>>(
+            n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out, count_out, status_out);
         const int grid2 = grid_for(reinterpret_cast<const void *>(ik::ik_redo_kernel<false>), 128, n * n_free);
         ik::ik_redo_kernel<false><<<grid2, 128, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, sols_out,
                                                          count_out, status_out);
