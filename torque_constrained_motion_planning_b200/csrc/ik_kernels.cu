@@ -35,7 +35,8 @@ constexpr int kSolRow = 57;
 // stalls per issue, 2.1 with solution sets).  Now ONE large CTA per SM: every iteration all lanes screen one solve each
 // (pose reduction + the j3 gate), survivors are appended to ONE shared-memory queue (block-level prefix over the warps'
 // ballots), and whenever the queue holds a CTA's worth of entries ALL warps solve at the same time -- they walk the
-// solver's code together, so one instruction fetch serves them all: 4.3 G solves/s counts only (+28 %).  Solution sets
+// solver's code together, so one instruction fetch serves them all: 4.3 G solves/s counts only (+28 %; 5.6 G with the
+// class queues below).  Solution sets
 // are staged in (dynamic) shared memory, one padded row per lane, and written row by row with coalesced stores.
 __device__ __forceinline__ void load_pose(int64_t s, int64_t n, int n_free, int free_broadcast,
                                           const double *__restrict__ rot9, const double *__restrict__ trans3,
@@ -49,67 +50,52 @@ __device__ __forceinline__ void load_pose(int64_t s, int64_t n, int n_free, int 
     prepare_pose(R, __ldg(trans3 + p), __ldg(trans3 + n + p), __ldg(trans3 + 2 * n + p), j6, P);
 }
 
+// The queue is split by WHICH j3 roots are live (ik_core.cuh plan_roots): both, only the first, only the second.  A
+// batch is taken from one class, so the solver's two-root loop runs both iterations with every lane busy, or skips the
+// same dead iteration on every lane (a warp-uniform branch) -- a mixed warp would execute both iterations with half of
+// its one-root lanes idle in each.  ~48 % of the surviving solves have two live roots, ~52 % one.
+#ifndef TCMP_IK_CLASSES
+#define TCMP_IK_CLASSES 3     // 1 = single queue (screen on the j3 gate only)
+#endif
 template <int THREADS, bool WRITE_SOLS>
 __global__ void __launch_bounds__(THREADS, 1)
 ik_kernel_cta(int64_t n, int n_free, int free_broadcast, const double *__restrict__ rot9,
               const double *__restrict__ trans3, const double *__restrict__ free_vals,
               double *__restrict__ sols_out, int32_t *__restrict__ count_out, uint8_t *__restrict__ status_out) {
     constexpr int kWarps = THREADS / 32;
-    extern __shared__ double rows[];                 // WRITE_SOLS: [THREADS][kSolRow]
-    __shared__ long long queue[2 * THREADS];         // <= THREADS - 1 left over + THREADS pushed per iteration
-    __shared__ int warp_cnt[kWarps];
+    constexpr int kClasses = TCMP_IK_CLASSES;
+    extern __shared__ double rows[];                        // WRITE_SOLS: [THREADS][kSolRow]
+    __shared__ long long queue[kClasses][2 * THREADS];      // per class: <= THREADS - 1 left over + THREADS pushed
+    __shared__ int warp_cnt[kClasses][kWarps];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t total = n * n_free;
     const int64_t per_iter = (int64_t)gridDim.x * THREADS;
     const int64_t n_iter = (total + per_iter - 1) / per_iter;     // the same trip count for every thread (barriers inside)
-    int qn = 0;                                                   // CTA-uniform queue length
-    for (int64_t it = 0; it <= n_iter; ++it) {
-        const bool last = it == n_iter;                           // one extra pass drains the queue
-        bool go = false, dead = false;
-        long long s = -1;
-        if (!last) {
-            s = (it * gridDim.x + blockIdx.x) * THREADS + tid;
-            if (s < total) {
-                Pose P;
-                load_pose(s, n, n_free, free_broadcast, rot9, trans3, free_vals, P);
-                const int verdict = screen_pose(P);
-                go = verdict == 1;
-                dead = !go;
-                if (dead) {
-                    count_out[s] = 0;
-                    if (status_out) status_out[s] = (uint8_t)(verdict == 2 ? kStatusInvalid : 0);
-                }
-            }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, go);
-        if (lane == 0) warp_cnt[wib] = __popc(m);
-        if (WRITE_SOLS) {   // zero-fill the rejected solves' slots: each warp its own 32 consecutive solves, coalesced
-            unsigned m_dead = __ballot_sync(0xffffffffu, dead);
-            const long long s0 = s - lane;                        // the warp's first solve of this iteration
-            while (m_dead) {
-                const int r = __ffs(m_dead) - 1;
-                m_dead &= m_dead - 1;
-                double *dst = sols_out + (__shfl_sync(0xffffffffu, s0, 0) + r) * 56;
-                dst[lane] = 0.0;
-                if (lane < 24) dst[32 + lane] = 0.0;
-            }
-        }
-        __syncthreads();
-        int before = 0, added = 0;
+    int qn[kClasses];                                             // CTA-uniform queue lengths
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const int cw = warp_cnt[w];
-            if (w < wib) before += cw;
-            added += cw;
+    for (int k = 0; k < kClasses; ++k) qn[k] = 0;
+    int64_t it = 0;
+    for (;;) {
+        // ---- pick a full class, or (once every solve has been screened) any non-empty one; else screen more ----
+        int cls = -1, take = 0;
+#pragma unroll
+        for (int k = 0; k < kClasses; ++k)
+            if (cls < 0 && qn[k] >= THREADS) { cls = k; take = THREADS; }
+        if (cls < 0 && it >= n_iter) {
+#pragma unroll
+            for (int k = 0; k < kClasses; ++k)
+                if (cls < 0 && qn[k] > 0) { cls = k; take = qn[k]; }
+            if (cls < 0) break;
         }
-        if (go) queue[qn + before + __popc(m & lt_mask)] = s;
-        qn += added;
-        __syncthreads();
-        const int take = last ? qn : (qn >= THREADS ? THREADS : 0);     // CTA-uniform
-        if (take > 0) {
+        if (cls >= 0) {
+            // ---- solve `take` entries of class `cls`, one per thread: all warps enter the solver together ----
+            long long *q = queue[0];
+#pragma unroll
+            for (int k = 1; k < kClasses; ++k)
+                if (cls == k) q = queue[k];
             if (tid < take) {
-                const long long sq = queue[tid];
+                const long long sq = q[tid];
                 Pose P;
                 load_pose(sq, n, n_free, free_broadcast, rot9, trans3, free_vals, P);
                 Emit out;
@@ -129,20 +115,83 @@ ik_kernel_cta(int64_t n, int n_free, int free_broadcast, const double *__restric
             if (WRITE_SOLS) {
                 __syncthreads();
                 for (int r = wib; r < take; r += kWarps) {   // row r -> its solve's 448 B slot: two coalesced stores
-                    double *dst = sols_out + queue[r] * 56;
+                    double *dst = sols_out + q[r] * 56;
                     dst[lane] = rows[r * kSolRow + lane];
                     if (lane < 24) dst[32 + lane] = rows[r * kSolRow + 32 + lane];
                 }
             }
-            const int rest = qn - take;
+            int rest = 0;
+#pragma unroll
+            for (int k = 0; k < kClasses; ++k)
+                if (cls == k) { rest = qn[k] - take; qn[k] = rest; }
             long long carry = 0;
             __syncthreads();
-            if (tid < rest) carry = queue[take + tid];
+            if (tid < rest) carry = q[take + tid];
             __syncthreads();
-            if (tid < rest) queue[tid] = carry;
-            qn = rest;
+            if (tid < rest) q[tid] = carry;
             __syncthreads();
+            continue;
         }
+        // ---- screen one solve per thread ----
+        const long long s = (it * gridDim.x + blockIdx.x) * THREADS + tid;
+        ++it;
+        int my = -1;          // class of this lane's solve, -1 = finished here (no live root) or out of range
+        bool dead = false;
+        if (s < total) {
+            Pose P;
+            load_pose(s, n, n_free, free_broadcast, rot9, trans3, free_vals, P);
+            unsigned status = 0;
+            if (kClasses == 1) {
+                const int verdict = screen_pose(P);
+                my = verdict == 1 ? 0 : -1;
+                status = verdict == 2 ? kStatusInvalid : 0;
+            } else {
+                Emit out;
+                out.sols = nullptr;
+                out.count = 0;
+                out.status = 0;
+                RootPlan pl;
+                const int n_live = plan_roots(P, pl, out);
+                my = n_live == 2 ? 0 : (n_live == 1 ? (pl.live[0] ? 1 : 2) : -1);
+                status = out.status;
+            }
+            dead = my < 0;
+            if (dead) {
+                count_out[s] = 0;
+                if (status_out) status_out[s] = (uint8_t)status;
+            }
+        }
+        unsigned mk[kClasses];
+#pragma unroll
+        for (int k = 0; k < kClasses; ++k) {
+            mk[k] = __ballot_sync(0xffffffffu, my == k);
+            if (lane == 0) warp_cnt[k][wib] = __popc(mk[k]);
+        }
+        if (WRITE_SOLS) {   // zero-fill the finished solves' slots: each warp its own 32 consecutive solves, coalesced
+            unsigned m_dead = __ballot_sync(0xffffffffu, dead);
+            const long long s0 = __shfl_sync(0xffffffffu, s, 0);   // the warp's first solve of this iteration
+            while (m_dead) {
+                const int r = __ffs(m_dead) - 1;
+                m_dead &= m_dead - 1;
+                double *dst = sols_out + (s0 + r) * 56;
+                dst[lane] = 0.0;
+                if (lane < 24) dst[32 + lane] = 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kClasses; ++k) {
+            int before = 0, added = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const int cw = warp_cnt[k][w];
+                if (w < wib) before += cw;
+                added += cw;
+            }
+            if (my == k) queue[k][qn[k] + before + __popc(mk[k] & lt_mask)] = s;
+            qn[k] += added;
+        }
+        __syncthreads();
     }
 }
 
