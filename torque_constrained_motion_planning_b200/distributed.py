@@ -156,7 +156,8 @@ class _DevArray:
 
 
 class PeerMaskBuffer:
-    """Gathered feasibility-mask buffer ``[world][n_per_rank]`` that every rank's torque kernel writes into
+    """Gathered feasibility-mask buffer ``[SLOTS][world][n_per_rank]`` (``gathered`` = the copy of the latest step,
+    ``[world][n_per_rank]``) that every rank's torque kernel writes into
     DIRECTLY (tcmp_rne_batch_scatter): the all-gather of the masks fused into the producing kernel as a
     peer-store epilogue over NVLink/NVSwitch.  Each rank allocates its copy with tcmp_peer_alloc (cudaMalloc +
     CUDA IPC), the 64-byte handles are exchanged once through torch.distributed, and peers are mapped with
@@ -174,8 +175,8 @@ class PeerMaskBuffer:
     before a capture so no event recorded outside the capture is waited on inside).
 
     ``barrier()`` (stream sync + torch.distributed barrier) remains for callers that synchronise on the host: with one
-    barrier per step, step i + 1's writes go to another copy than step i's, and a copy is written again only two
-    barriers later, so readers of step i must be done before they enter the barrier of step i + 1.  (With a single
+    barrier per step, step i + 1's writes go to another copy than step i's, and a copy is written again only three
+    steps later, so readers of step i have until they enter the barrier of step i + 2.  (With a single
     copy a fast rank's next step could overwrite a row a slower rank was still reading: ADVICE r01.)"""
 
     itemsize = 1
