@@ -37,3 +37,17 @@ for rep in range(6):
 torch.cuda.synchronize()
 assert torch.equal(own[:N_STATES], mask) and torch.equal(peer[:N_STATES].to("cuda:0"), mask)
 print("ok: plain and scatter masks agree on both devices")
+# the edge kernel with IndexDests (tcmp_edge_feasibility_scatter): configs[3], first-failure indices to both devices
+from bench import sample_edges  # noqa: E402
+E, W = 100_000, 64
+qa, qb = (torch.as_tensor(a, device="cuda:0") for a in sample_edges(E, 4))
+own_i = torch.full((E,), -1, dtype=torch.int32, device="cuda:0")
+peer_i = torch.full((E,), -1, dtype=torch.int32, device="cuda:1")
+peer_i.copy_(own_i)
+iptrs = (ctypes.c_void_p * 2)(own_i.data_ptr(), peer_i.data_ptr())
+for rep in range(4):
+    ff = engine.edge_feasibility(qa, qb, W, 5.0, mode="rne")
+    _lib.check(lib.tcmp_edge_feasibility_scatter(0, E, W, qa.data_ptr(), qb.data_ptr(), 5.0, 0.01, 0, 2, iptrs, 0, None))
+torch.cuda.synchronize()
+assert torch.equal(own_i, ff) and torch.equal(peer_i.to("cuda:0"), ff)
+print("ok: plain and scatter first-failure indices agree on both devices")
