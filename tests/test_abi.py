@@ -151,6 +151,7 @@ def test_library_carries_sm_100a_code_for_every_kernel_family():
     cubins = re.findall(r"(\w+)\.(sm_\w+)\.cubin", elfs)
     assert cubins and {arch for _, arch in cubins} == {"sm_100a"}, elfs
     usage = subprocess.run([cuobjdump, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    for kernel in ("rne_batch_kernel", "rne_model_kernel", "edge_kernel", "traj_kernel", "ik_kernel_compact",
-                   "fk_kernel", "ik_select_kernel", "collision_kernel", "extend_prefix_kernel", "fp64_peak_kernel"):
+    for kernel in ("rne_batch_kernel", "rne_model_kernel", "edge_kernel", "traj_kernel", "ik_kernel_cta", "ik_redo_kernel",
+                   "fk_kernel", "ik_select_kernel", "collision_kernel", "extend_prefix_kernel", "peer_signal_kernel",
+                   "peer_wait_kernel", "peer_push_kernel", "fp64_peak_kernel"):
         assert kernel in usage, kernel
