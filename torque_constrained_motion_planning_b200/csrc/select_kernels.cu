@@ -32,7 +32,18 @@ struct JointLimits {
 //      prefix -- the list is in sweep order.
 //   B. lanes own CANDIDATES: one static torque test each (dense), then a shuffle arg-min over (cost, key) picks
 //      the nearest feasible configuration; ties go to the earliest key, as a serial scan in sweep order would.
-constexpr int kSelWarps = 2;            // warps per CTA
+// Round 2 (profiles/r02/select_variants.log): one 8-warp CTA per SM with CTA barriers at the phase boundaries, so that
+// all warps of the SM walk the solver's ~60 KB of code together (as the CTA-wide IK sweep kernel does), against
+// 4 independent 2-warp CTAs per SM at the same occupancy: 0.89 -> 1.10 G solves/s (rne, 25 free values), outputs
+// bit-identical.  Barriers alone at 2 / 4 warps: 0.99 / 1.03; 4 warps without barriers: 0.91.
+#ifndef TCMP_SEL_WARPS
+#define TCMP_SEL_WARPS 8
+#endif
+#ifndef TCMP_SEL_ALIGN
+#define TCMP_SEL_ALIGN 1
+#endif
+constexpr int kSelWarps = TCMP_SEL_WARPS;   // warps per CTA (8: 147 KB of candidate lists, dynamic shared memory)
+constexpr bool kSelAlign = TCMP_SEL_ALIGN;  // CTA barriers at the phase boundaries
 constexpr int kSelCap = 256;            // 32 lanes x 8 solutions: a round can never overflow the list
 constexpr int kSelRow = 9;              // q[7], cost, key (as double) -- odd stride, conflict-free 64-bit rows
 
@@ -43,15 +54,20 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
                  const double *__restrict__ q_ref, int ref_broadcast, JointLimits lim, int check_torque,
                  double mass, double payload_threshold, int use_max_norm, double *__restrict__ best_q,
                  double *__restrict__ best_cost, int32_t *__restrict__ n_valid, const __grid_constant__ P prm) {
-    __shared__ double cand_all[kSelWarps][kSelCap * kSelRow];
+    extern __shared__ double cand_all[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double *cand = cand_all[wib];
+    double *cand = cand_all + wib * (kSelCap * kSelRow);
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double mp_inertial = TOOL ? 0.0 : (mass > payload_threshold ? mass : 0.0);
     const double mp_tool = TOOL ? mass : 0.0;
     const unsigned lt_mask = (1u << lane) - 1u;
-    for (int64_t p = warp; p < n; p += n_warps) {
+    // kSelAlign: the trip count is CTA-uniform (a warp past the end repeats the last pose and writes nothing), so the
+    // barriers below are reached by every thread.
+    const int64_t p_end = kSelAlign ? ((n + n_warps - 1) / n_warps) * n_warps : n;
+    for (int64_t p0 = warp; p0 < p_end; p0 += n_warps) {
+        const bool act = p0 < n;
+        const int64_t p = act ? p0 : n - 1;
         double R[9], ref[7];
 #pragma unroll
         for (int i = 0; i < 9; ++i) R[i] = __ldg(rot9 + i * n + p);
@@ -63,6 +79,7 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
         double bq[7] = {0, 0, 0, 0, 0, 0, 0};
         for (int fbase = 0; fbase < n_free; fbase += 32) {
             // ---- phase A: IK + joint-limit filter for up to 32 free values ----
+            if (kSelAlign) __syncthreads();
             const int f = fbase + lane;
             double sols[56];
             int cnt = 0;
@@ -106,7 +123,7 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
                 }
                 ncand += __popc(m);
             }
-            __syncwarp();
+            if (kSelAlign) __syncthreads(); else __syncwarp();
             // ---- phase B: one candidate per lane, dense static torque tests ----
             for (int c = lane; c < ncand; c += 32) {
                 const double *row = cand + c * kSelRow;
@@ -145,7 +162,7 @@ ik_select_kernel(int64_t n, int n_free, int free_broadcast, const double *__rest
             valid += __shfl_xor_sync(0xffffffffu, valid, off);
             if (oc < bc || (oc == bc && ok2 < bk) || (oc == bc && ok2 == bk && ol < bl)) { bc = oc; bk = ok2; bl = ol; }
         }
-        if (lane == bl) {       // with no survivor every lane ties at (inf, INT_MAX): lane 0 writes zeros
+        if (lane == bl && act) {       // with no survivor every lane ties at (inf, INT_MAX): lane 0 writes zeros
 #pragma unroll
             for (int j = 0; j < 7; ++j) best_q[j * n + p] = bq[j];
             best_cost[p] = bc;
@@ -161,8 +178,17 @@ static cudaError_t launch_select_p(int64_t n, const double *rot9, const double *
                                    int use_max_norm, double *best_q, double *best_cost, int32_t *n_valid, const P &prm,
                                    cudaStream_t st) {
     auto kern = ik_select_kernel<TOOL, P>;
-    const int grid = grid_for(reinterpret_cast<const void *>(kern), kSelWarps * 32, n * 32, kSelWaves);
-    kern<<<grid, kSelWarps * 32, 0, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref, ref_broadcast, lim,
+    constexpr int smem = kSelWarps * kSelCap * kSelRow * (int)sizeof(double);
+    if (smem > 48 * 1024) {   // wider CTAs only (per device, so set on the launching one)
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSelWarps * 32, smem) != cudaSuccess || per_sm <= 0)
+        per_sm = 1;
+    const int64_t full = (int64_t)sm_count() * per_sm * kSelWaves, want = (n + kSelWarps - 1) / kSelWarps;
+    const int grid = (int)(want < full ? want : full);
+    kern<<<grid, kSelWarps * 32, smem, st>>>(n, n_free, free_broadcast, rot9, trans3, free_vals, q_ref, ref_broadcast, lim,
                                           check, mass, payload_threshold, use_max_norm, best_q, best_cost, n_valid, prm);
     return cudaGetLastError();
 }
